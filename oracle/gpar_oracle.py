@@ -1,0 +1,769 @@
+"""CPU oracle for the GPAR per-layer GP hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module restates, in numpy/scipy fp64, the algorithm that wesselb/gpar runs
+through stheno/mlkernels/matrix/lab on torch-CPU.  It is the *checker* for the
+CUDA engine in ``gpar_b200`` and the timed "port" CPU baseline of ``bench.py``.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import it.  The product package never does.
+
+PARITY STATUS
+-------------
+* Integer / boolean path (``per_output``, ``merge``, ``last``,
+  ``determine_indices``): pinned bit-exactly against the golden vectors of the
+  reference's own tests (tests/test_model.py:30-38, 46-52, 55-100;
+  tests/test_regression.py:52-83) -- see tests/test_oracle_golden.py.
+* Floating-point path: **parity unpinned**.  The arithmetic of the reference
+  lives in third-party packages (stheno>=1.1, mlkernels, backends-matrix>=1,
+  backends/lab>=1, varz>=0.6; lower bounds only, reference setup.py:3-12) which
+  are neither vendored under /root/reference nor installable here, and the
+  reference's tests hold no stored floating-point vectors.  The restatement is
+  therefore anchored on (i) every *relational* known answer of the reference's
+  tests (tests/test_model.py:118-293, tests/test_regression.py:92-208) and (ii)
+  independent scipy/textbook identities (scipy.stats.multivariate_normal,
+  inv-based VFE).  Choices that the reference's tests do not pin are marked
+  [UNPINNED] below.
+
+Control flow follows gpar/model.py and gpar/regression.py line by line; every
+function cites the lines it restates.
+"""
+import math
+
+import numpy as np
+import scipy.linalg as sla
+
+__all__ = [
+    "EPSILON",
+    "merge",
+    "last",
+    "per_output",
+    "determine_indices",
+    "vector_from_init",
+    "kernel_matrix",
+    "GP",
+    "Obs",
+    "PseudoObs",
+    "FDD",
+    "GPAR",
+    "OracleRegressor",
+    "Normals",
+    "log_transform",
+    "squishing_transform",
+]
+
+#: Diagonal jitter added inside every Cholesky (``B.epsilon`` of lab; default
+#: 1e-12 [UPSTREAM-RECALL]; examples/paper/air_temp.py:18 shows it is a mutable
+#: global).
+EPSILON = 1e-12
+
+
+# --------------------------------------------------------------------------
+# Index / mask helpers (bit-exact contract)
+# --------------------------------------------------------------------------
+
+
+def merge(x, updates, to_update):
+    """gpar/model.py:14-44.  result[i] = updates[rank of i among True] if
+    to_update[i] else x[i].  The reference builds the index list with a Python
+    loop; this is the same permutation, vectorised."""
+    x = np.asarray(x)
+    updates = np.asarray(updates)
+    to_update = np.asarray(to_update, dtype=bool)
+    concat = np.concatenate([x[~to_update], updates], axis=0)
+    n_keep = int(np.sum(~to_update))
+    indices = np.empty(len(to_update), dtype=np.int64)
+    indices[~to_update] = np.arange(n_keep)
+    indices[to_update] = n_keep + np.arange(int(np.sum(to_update)))
+    return concat[indices]
+
+
+def last(xs, select=None):
+    """gpar/model.py:60-93.  Zip with an is-last flag; ``select`` filters by
+    index but the flag refers to the unfiltered sequence."""
+    if select is not None:
+        select = set(select)
+    saved_x = None
+    i = -1
+
+    def should_yield(i_):
+        return i >= 0 and (select is None or i_ in select)
+
+    for x in xs:
+        if should_yield(i):
+            yield False, saved_x
+        saved_x = x
+        i += 1
+    if saved_x is not None and should_yield(i):
+        yield True, saved_x
+
+
+def per_output(y, w, keep=False):
+    """gpar/model.py:325-368.  Closed-downwards per-output split.  ``y`` may be
+    a dict cache (model.py:365-368) keyed by ``keep``."""
+    if isinstance(y, dict):
+        for yi in y[keep]:
+            yield yi
+        return
+    y = np.asarray(y)
+    w = np.asarray(w)
+    p = y.shape[1]
+    available = ~np.isnan(y)
+    for i in range(p):
+        mask = available[:, i]
+        if keep and i < p - 1:
+            mask = mask | np.any(available[:, i + 1 :], axis=1)
+        yield y[mask, i : i + 1], w[mask, i], mask
+        y = y[mask]
+        w = w[mask]
+        available = available[mask]
+
+
+def determine_indices(m, pi, markov):
+    """gpar/regression.py:49-59."""
+    p_last = pi - 1
+    p_start = 0 if markov is None else max(p_last - (markov - 1), 0)
+    p_num = p_last - p_start + 1
+    m_inds = list(range(m))
+    p_inds = list(range(m + p_start, m + p_last + 1))
+    return m_inds, p_inds, p_num
+
+
+def vector_from_init(init, length):
+    """gpar/regression.py:31-46."""
+    if np.size(init) == 1:
+        return init * np.ones(length)
+    init_squeezed = np.squeeze(init)
+    if np.ndim(init_squeezed) != 1:
+        raise ValueError("Incorrect shape {} of hyperparameters.".format(np.shape(init)))
+    if np.size(init_squeezed) < length:
+        raise ValueError("Not enough hyperparameters specified.")
+    return np.array(init_squeezed)[:length]
+
+
+# --------------------------------------------------------------------------
+# Kernel evaluation (mlkernels restated)
+# --------------------------------------------------------------------------
+#
+# A kernel is a list of *terms* (dicts).  Term types and formulas:
+#   "eq":       var * exp(-1/2 * sum_c ((x_c - y_c) / s_c)^2)
+#   "rq":       var * (1 + sum_c ((x_c - y_c)/s_c)^2 / (2 alpha))^(-alpha)
+#   "linear":   var * sum_c (x_c / s_c) (y_c / s_c)
+#   "const":    var
+#   "periodic": var * exp(-1/2 * sum_c [ ((sin(2 pi x_c/T_c) - sin(2 pi y_c/T_c)) / s_c)^2
+#                                      + ((cos(2 pi x_c/T_c) - cos(2 pi y_c/T_c)) / s_{m+c})^2 ])
+#                   * exp(-1/2 * sum_c ((x_c - y_c) / d_c)^2)
+#     i.e. EQ().stretch(scales[2m]).periodic(periods) * EQ().stretch(decays)
+#     (regression.py:113-129) with the feature map u(x) = [sin block, cos block]
+#     [UNPINNED: block ordering of the periodic feature map].
+# "cols" selects columns of the input (``.select``; regression.py:176-179).
+# Squared distances use the direct difference form and are never clipped.
+
+
+def _sqdist(X, Y, cols, inv_scale):
+    d2 = np.zeros((X.shape[0], Y.shape[0]))
+    for c, s in zip(cols, inv_scale):
+        diff = (X[:, c][:, None] - Y[:, c][None, :]) * s
+        d2 += diff * diff
+    return d2
+
+
+def kernel_matrix(terms, X, Y):
+    """K[i, j] = sum_t k_t(X[i], Y[j]) for the closed kernel family emitted by
+    gpar/regression.py:92-180."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    K = np.zeros((X.shape[0], Y.shape[0]))
+    for t in terms:
+        kind = t["type"]
+        var = float(t.get("variance", 1.0))
+        cols = list(t.get("cols", []))
+        if kind == "const":
+            K += var
+            continue
+        inv_scale = 1.0 / np.asarray(t["scales"], dtype=np.float64)
+        if kind == "eq":
+            K += var * np.exp(-0.5 * _sqdist(X, Y, cols, inv_scale))
+        elif kind == "rq":
+            alpha = float(t["alpha"])
+            K += var * (1.0 + _sqdist(X, Y, cols, inv_scale) / (2.0 * alpha)) ** (-alpha)
+        elif kind == "linear":
+            acc = np.zeros_like(K)
+            for c, s in zip(cols, inv_scale):
+                acc += (X[:, c] * s)[:, None] * (Y[:, c] * s)[None, :]
+            K += var * acc
+        elif kind == "periodic":
+            m = len(cols)
+            freq = 2.0 * np.pi / np.asarray(t["periods"], dtype=np.float64)
+            inv_decay = 1.0 / np.asarray(t["decays"], dtype=np.float64)
+            d2 = np.zeros_like(K)
+            for j, c in enumerate(cols):
+                ax, ay = X[:, c] * freq[j], Y[:, c] * freq[j]
+                ds = (np.sin(ax)[:, None] - np.sin(ay)[None, :]) * inv_scale[j]
+                dc = (np.cos(ax)[:, None] - np.cos(ay)[None, :]) * inv_scale[m + j]
+                d2 += ds * ds
+                d2 += dc * dc
+            K += var * np.exp(-0.5 * d2) * np.exp(-0.5 * _sqdist(X, Y, cols, inv_decay))
+        else:
+            raise ValueError(f"unknown kernel term {kind!r}")
+    return K
+
+
+# --------------------------------------------------------------------------
+# GP algebra (stheno/matrix restated)
+# --------------------------------------------------------------------------
+
+
+def _chol(a):
+    """matrix.cholesky(Dense): chol(a + eps I), lower."""
+    a = np.array(a, dtype=np.float64, copy=True)
+    a[np.diag_indices_from(a)] += EPSILON
+    return sla.cholesky(a, lower=True, check_finite=False)
+
+
+def _solve_lower(L, b):
+    return sla.solve_triangular(L, b, lower=True, check_finite=False)
+
+
+class Normals:
+    """Source of standard normals.  Either replays injected arrays in draw
+    order (for parity runs) or draws from a numpy Generator.  Draw order is the
+    reference's: layer-major; with ``latent=True`` first the latent draw, then
+    the noise draw (gpar/model.py:264-266)."""
+
+    def __init__(self, rng=None, queue=None):
+        self.rng = np.random.default_rng() if (rng is None and queue is None) else rng
+        self.queue = None if queue is None else [np.asarray(q, dtype=np.float64) for q in queue]
+        self.pos = 0
+
+    def __call__(self, n):
+        if self.queue is not None:
+            z = self.queue[self.pos]
+            self.pos += 1
+            if z.size != n:
+                raise ValueError(f"injected normal #{self.pos - 1} has size {z.size}, need {n}")
+            return z.reshape(n, 1)
+        return self.rng.standard_normal((n, 1))
+
+
+class GP:
+    """Zero-mean prior GP with a term-list kernel, or a posterior of one.
+
+    ``GP(terms)``                      prior (stheno ``GP(kernel, measure=...)``)
+    ``f | Obs(...)`` / ``f | PseudoObs(...)``  posterior (model.py:170,232,298)
+    """
+
+    def __init__(self, terms=None, parent=None, obs=None):
+        self.terms = terms
+        self.parent = parent
+        self.obs = obs
+        self._cache = None
+
+    # -- prior / posterior moments ------------------------------------
+    def mean(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        if self.parent is None:
+            return np.zeros((x.shape[0], 1))
+        return self.parent.mean(x) + self.obs.posterior_mean_correction(self.parent, x)
+
+    def kernel(self, x, y):
+        if self.parent is None:
+            return kernel_matrix(self.terms, x, y)
+        return self.parent.kernel(x, y) - self.obs.posterior_kernel_correction(self.parent, x, y)
+
+    def kernel_diag(self, x):
+        """diag(kernel(x, x)) without forming the square."""
+        x = np.asarray(x, dtype=np.float64)
+        if self.parent is None:
+            out = np.zeros(x.shape[0])
+            for t in self.terms:
+                var = float(t.get("variance", 1.0))
+                if t["type"] == "linear":
+                    inv = 1.0 / np.asarray(t["scales"], dtype=np.float64)
+                    out += var * np.sum((x[:, list(t["cols"])] * inv[None, :]) ** 2, axis=1)
+                else:  # eq, rq, periodic, const: k(x, x) = var
+                    out += var
+            return out
+        return self.parent.kernel_diag(x) - self.obs.posterior_kernel_diag_correction(self.parent, x)
+
+    # -- protocol -----------------------------------------------------
+    def __call__(self, x, noise=None):
+        return FDD(self, x, noise)
+
+    def __or__(self, obs):
+        return GP(parent=self, obs=obs)
+
+    def logpdf(self, obs):
+        """``f.measure.logpdf(obs)`` (model.py:226)."""
+        return obs.logpdf(self)
+
+
+class FDD:
+    """Finite-dimensional distribution ``f(x, noise)``: noise is None, a scalar
+    or a vector (the reference passes the vector ``noise / w``, model.py:287)."""
+
+    def __init__(self, f, x, noise=None):
+        self.f = f
+        self.x = np.asarray(x, dtype=np.float64)
+        if self.x.ndim == 1:
+            self.x = self.x[:, None]
+        n = self.x.shape[0]
+        if noise is None:
+            self.noise = np.zeros(n)
+        else:
+            self.noise = np.broadcast_to(np.asarray(noise, dtype=np.float64), (n,)).copy()
+
+    def var(self):
+        K = self.f.kernel(self.x, self.x)
+        K[np.diag_indices_from(K)] += self.noise
+        return K
+
+    def logpdf(self, y):
+        """Normal.logpdf: -1/2 (logdet + n log 2pi + ||L^-1 (y - m)||^2)."""
+        y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+        n = y.shape[0]
+        if n == 0:
+            return 0.0
+        L = _chol(self.var())
+        u = _solve_lower(L, y - self.f.mean(self.x))
+        logdet = 2.0 * np.sum(np.log(np.diag(L)))
+        return float(-0.5 * (logdet + n * math.log(2.0 * math.pi) + np.sum(u * u)))
+
+    def sample(self, normals):
+        """Normal.sample: mean + chol(var + eps I) z (joint draw)."""
+        n = self.x.shape[0]
+        if n == 0:
+            return np.zeros((0, 1))
+        L = _chol(self.var())
+        return self.f.mean(self.x) + L @ normals(n)
+
+
+class Obs:
+    """Dense observations ``Obs(f(x, noise), y)``; posterior per SURVEY 8(c)-3:
+    mean(x_) = m(x_) + (L^-1 K(x_a, x_))^T L^-1 (y - m(x_a)) with a fresh
+    triangular solve per call (no alpha cache) -- the reference-faithful op
+    sequence that the CPU baseline times."""
+
+    def __init__(self, fdd, y):
+        self.fdd = fdd
+        self.y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+        self._L = None
+
+    def __bool__(self):
+        return True
+
+    def _chol_of(self, f):
+        if self._L is None:
+            K = f.kernel(self.fdd.x, self.fdd.x)
+            K[np.diag_indices_from(K)] += self.fdd.noise
+            self._L = _chol(K)
+        return self._L
+
+    def logpdf(self, f):
+        """Dense log-marginal.  The factor is shared with the
+        posterior built from the same observations (one Cholesky per layer)."""
+        n = self.y.shape[0]
+        if n == 0:
+            return 0.0
+        L = self._chol_of(f)
+        u = _solve_lower(L, self.y - f.mean(self.fdd.x))
+        logdet = 2.0 * np.sum(np.log(np.diag(L)))
+        return float(-0.5 * (logdet + n * math.log(2.0 * math.pi) + np.sum(u * u)))
+
+    def posterior_mean_correction(self, f, x):
+        if self.y.shape[0] == 0:
+            return np.zeros((x.shape[0], 1))
+        L = self._chol_of(f)
+        A = _solve_lower(L, f.kernel(self.fdd.x, x))
+        b = _solve_lower(L, self.y - f.mean(self.fdd.x))
+        return A.T @ b
+
+    def posterior_kernel_correction(self, f, x, y):
+        if self.y.shape[0] == 0:
+            return np.zeros((x.shape[0], y.shape[0]))
+        L = self._chol_of(f)
+        A = _solve_lower(L, f.kernel(self.fdd.x, x))
+        Bm = A if y is x else _solve_lower(L, f.kernel(self.fdd.x, y))
+        return A.T @ Bm
+
+    def posterior_kernel_diag_correction(self, f, x):
+        if self.y.shape[0] == 0:
+            return np.zeros(x.shape[0])
+        A = _solve_lower(self._chol_of(f), f.kernel(self.fdd.x, x))
+        return np.sum(A * A, axis=0)
+
+
+class PseudoObs:
+    """VFE / Titsias inducing-point observations ``PseudoObs(f(z), f(x, noise), y)``
+    (model.py:286-287); formulas of SURVEY 8(a) row a9."""
+
+    def __init__(self, fdd_u, fdd, y):
+        self.fdd_u = fdd_u
+        self.fdd = fdd
+        self.y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+        self._c = None
+
+    def __bool__(self):
+        return True
+
+    def _compute(self, f):
+        if self._c is None:
+            z, x, sig = self.fdd_u.x, self.fdd.x, self.fdd.noise
+            L_z = _chol(f.kernel(z, z))
+            Bm = _solve_lower(L_z, f.kernel(z, x))  # (M, n)
+            A = np.eye(z.shape[0]) + (Bm / sig[None, :]) @ Bm.T
+            L_A = sla.cholesky(A, lower=True, check_finite=False)
+            ybar = self.y - f.mean(x)
+            c = Bm @ (ybar / sig[:, None])  # L_z^-1 K_zx Sigma^-1 ybar
+            LA_inv_c = _solve_lower(L_A, c)
+            # mu = m_z + L_z A^-1 c
+            A_inv_c = sla.solve_triangular(L_A.T, LA_inv_c, lower=False, check_finite=False)
+            mu = f.mean(z) + L_z @ A_inv_c
+            kdiag = f.kernel_diag(x)
+            trace_term = np.sum((kdiag - np.sum(Bm * Bm, axis=0)) / sig)
+            logdet_A = 2.0 * np.sum(np.log(np.diag(L_A)))
+            elbo = -0.5 * (
+                trace_term
+                + np.sum(np.log(2.0 * math.pi * sig))
+                + logdet_A
+                + np.sum(ybar * ybar / sig[:, None])
+                - np.sum(LA_inv_c * LA_inv_c)
+            )
+            self._c = dict(L_z=L_z, L_A=L_A, mu=mu, elbo=float(elbo))
+        return self._c
+
+    def logpdf(self, f):
+        if self.y.shape[0] == 0:
+            return 0.0
+        return self._compute(f)["elbo"]
+
+    def posterior_mean_correction(self, f, x):
+        c = self._compute(f)
+        z = self.fdd_u.x
+        # K_xz L_z^-T L_z^-1 (mu - m_z)
+        t = _solve_lower(c["L_z"], c["mu"] - f.mean(z))
+        Bx = _solve_lower(c["L_z"], f.kernel(z, x))
+        return Bx.T @ t
+
+    def posterior_kernel_correction(self, f, x, y):
+        c = self._compute(f)
+        z = self.fdd_u.x
+        Bx = _solve_lower(c["L_z"], f.kernel(z, x))
+        By = Bx if y is x else _solve_lower(c["L_z"], f.kernel(z, y))
+        # k - Bx^T By + Bx^T A^-1 By  => correction = Bx^T By - Bx^T A^-1 By
+        Ax = _solve_lower(c["L_A"], Bx)
+        Ay = Ax if y is x else _solve_lower(c["L_A"], By)
+        return Bx.T @ By - Ax.T @ Ay
+
+    def posterior_kernel_diag_correction(self, f, x):
+        c = self._compute(f)
+        Bx = _solve_lower(c["L_z"], f.kernel(self.fdd_u.x, x))
+        Ax = _solve_lower(c["L_A"], Bx)
+        return np.sum(Bx * Bx, axis=0) - np.sum(Ax * Ax, axis=0)
+
+
+# --------------------------------------------------------------------------
+# GPAR model loop (gpar/model.py:96-322 restated)
+# --------------------------------------------------------------------------
+
+
+def construct_model(f, noise):
+    """gpar/model.py:47-57."""
+    return lambda: (f, noise)
+
+
+class GPAR:
+    """gpar/model.py:96-322 on numpy arrays.  Sampling methods take a
+    :class:`Normals` source instead of the reference's global torch RNG."""
+
+    def __init__(self, replace=False, impute=False, x_ind=None):
+        self.replace = replace
+        self.impute = impute
+        self.layers = []
+        self.sparse = x_ind is not None
+        self.x_ind = None if x_ind is None else x_ind
+
+    def copy(self):
+        return GPAR(replace=self.replace, impute=self.impute, x_ind=self.x_ind)
+
+    def add_layer(self, model_constructor):
+        gpar = self.copy()
+        gpar.layers = list(self.layers) + [model_constructor]
+        return gpar
+
+    def __or__(self, x_y_w):
+        """model.py:148-176."""
+        x, y, w = x_y_w
+        gpar, x_ind = self.copy(), self.x_ind
+        for is_last, ((y, w, mask), model) in last(zip(per_output(y, w, keep=self.impute), self.layers)):
+            x = x[mask]
+            f, noise = model()
+            obs = self._obs(x, x_ind, y, w, f, noise)
+            gpar.layers.append(construct_model(f | obs, noise))
+            if not is_last:
+                x, x_ind = self._update_inputs(x, x_ind, y, f, obs)
+        return gpar
+
+    def logpdf(
+        self,
+        x,
+        y,
+        w,
+        only_last_layer=False,
+        sample_missing=False,
+        return_inputs=False,
+        x_ind=None,
+        outputs=None,
+        normals=None,
+    ):
+        """model.py:178-243."""
+        logpdf = 0.0
+        x_ind = self.x_ind if x_ind is None else x_ind
+        y_per_output = per_output(y, w, keep=self.impute or sample_missing)
+        for is_last, ((y, w, mask), model) in last(zip(y_per_output, self.layers), select=outputs):
+            x = x[mask]
+            f, noise = model()
+            obs = self._obs(x, x_ind, y, w, f, noise)
+            if not only_last_layer or (is_last and only_last_layer):
+                logpdf = logpdf + f.logpdf(obs)
+            if not is_last:
+                missing = np.isnan(y[:, 0])
+                if sample_missing and np.any(missing):
+                    f_post = f | obs
+                    y = merge(y, f_post(x[missing], noise / w[missing]).sample(normals), missing)
+                x, x_ind = self._update_inputs(x, x_ind, y, f, obs)
+        return (x, x_ind) if return_inputs else logpdf
+
+    def sample(self, x, w, latent=False, normals=None):
+        """model.py:245-277."""
+        normals = Normals() if normals is None else normals
+        sample = np.zeros((x.shape[0], 0))
+        x_ind = self.x_ind
+        for i, (is_last, model) in enumerate(last(self.layers)):
+            f, noise = model()
+            if latent:
+                f_sample = f(x).sample(normals)
+                stds = np.sqrt(noise / w[:, i : i + 1])
+                y_sample = f_sample + stds * normals(f_sample.shape[0])
+                sample = np.concatenate([sample, f_sample], axis=1)
+            else:
+                y_sample = f(x, noise / w[:, i]).sample(normals)
+                sample = np.concatenate([sample, y_sample], axis=1)
+            if not is_last:
+                x, x_ind = self._update_inputs(x, x_ind, y_sample, f, None)
+        return sample
+
+    def _obs(self, x, x_ind, y, w, f, noise):
+        """model.py:279-289."""
+        available = ~np.isnan(y[:, 0])
+        x = x[available]
+        y = y[available]
+        w = w[available]
+        if self.sparse:
+            return PseudoObs(f(x_ind), f(x, noise / w), y)
+        else:
+            return Obs(f(x, noise / w), y)
+
+    def _update_inputs(self, x, x_ind, y, f, obs):
+        """model.py:291-322."""
+        available = ~np.isnan(y[:, 0])
+
+        def estimate(x_):
+            if obs:
+                f_post = f | obs
+                return f_post.mean(x_)
+            else:
+                return f.mean(x_)
+
+        if self.sparse:
+            x_ind = np.concatenate([x_ind, estimate(x_ind)], axis=1)
+        if self.impute and self.replace:
+            y = estimate(x)
+        else:
+            if self.impute and np.any(~available):
+                y = merge(y, estimate(x[~available]), ~available)
+            if self.replace and np.any(available):
+                y = merge(y, estimate(x[available]), available)
+        x = np.concatenate([x, y], axis=1)
+        return x, x_ind
+
+
+# --------------------------------------------------------------------------
+# Regressor (gpar/regression.py restated)
+# --------------------------------------------------------------------------
+
+log_transform = (np.log, np.exp)
+squishing_transform = (
+    lambda x: np.sign(x) * np.log(1 + np.abs(x)),
+    lambda x: np.sign(x) * (np.exp(np.abs(x)) - 1),
+)
+
+
+class _Vars:
+    """Minimal stand-in for varz.Vars: a name -> value store whose ``bnd``/``get``
+    return the stored value, initialising it on first use (regression.py:101-173).
+    Bounds only matter to ``fit`` and are recorded, not enforced here."""
+
+    def __init__(self):
+        self.values = {}
+        self.bounds = {}
+
+    def bnd(self, name, init, lower=1e-4, upper=1e4):
+        if name not in self.values:
+            self.values[name] = np.array(init, dtype=np.float64)
+            self.bounds[name] = (lower, upper)
+        return self.values[name]
+
+    def get(self, name, init):
+        if name not in self.values:
+            self.values[name] = np.array(init, dtype=np.float64)
+            self.bounds[name] = (None, None)
+        return self.values[name]
+
+
+def model_terms(vs, m, pi, scale, scale_tie, per, per_period, per_scale, per_decay, input_linear,
+                input_linear_scale, linear, linear_scale, nonlinear, nonlinear_scale, rq, markov, noise):
+    """Kernel recipe of gpar/regression.py:92-180 as a term list + noise."""
+    m_inds, p_inds, p_num = determine_indices(m, pi, markov)
+    terms = []
+    variance = vs.bnd(name=f"{pi}/input/var", init=1.0)
+    scales = vs.bnd(name=f"{0 if scale_tie else pi}/input/scales", init=vector_from_init(scale, m))
+    if rq:
+        alpha = vs.bnd(name=f"{pi}/input/alpha", init=1e-2, lower=1e-3, upper=1e3)
+        terms.append(dict(type="rq", variance=variance, cols=m_inds, scales=scales, alpha=alpha))
+    else:
+        terms.append(dict(type="eq", variance=variance, cols=m_inds, scales=scales))
+    if per:
+        variance = vs.bnd(name=f"{pi}/input/per/var", init=1.0)
+        scales = vs.bnd(name=f"{pi}/input/per/scales", init=vector_from_init(per_scale, 2 * m))
+        periods = vs.bnd(name=f"{pi}/input/per/pers", init=vector_from_init(per_period, m))
+        decays = vs.bnd(name=f"{pi}/input/per/decay", init=vector_from_init(per_decay, m))
+        terms.append(dict(type="periodic", variance=variance, cols=m_inds, scales=scales,
+                          periods=periods, decays=decays))
+    if input_linear:
+        scales = vs.bnd(name=f"{pi}/input/lin/scales", init=vector_from_init(input_linear_scale, m))
+        const = vs.get(name=f"{pi}/input/lin/const", init=1.0)
+        terms.append(dict(type="linear", variance=1.0, cols=m_inds, scales=scales))
+        terms.append(dict(type="const", variance=const))
+    if linear and pi > 0:
+        scales = vs.bnd(name=f"{pi}/output/lin/scales", init=vector_from_init(linear_scale, p_num))
+        terms.append(dict(type="linear", variance=1.0, cols=p_inds, scales=scales))
+    if nonlinear and pi > 0:
+        variance = vs.bnd(name=f"{pi}/output/nonlin/var", init=1.0)
+        scales = vs.bnd(name=f"{pi}/output/nonlin/scales", init=vector_from_init(nonlinear_scale, p_num))
+        if rq:
+            alpha = vs.bnd(name=f"{pi}/output/nonlin/alpha", init=1e-2, lower=1e-3, upper=1e3)
+            terms.append(dict(type="rq", variance=variance, cols=p_inds, scales=scales, alpha=alpha))
+        else:
+            terms.append(dict(type="eq", variance=variance, cols=p_inds, scales=scales))
+    noise_variance = vs.bnd(name=f"{pi}/noise", init=vector_from_init(noise, pi + 1)[pi], lower=1e-8)
+    return terms, float(noise_variance)
+
+
+def _uprank(a):
+    a = np.asarray(a, dtype=np.float64)
+    return a[:, None] if a.ndim == 1 else a
+
+
+class OracleRegressor:
+    """gpar/regression.py:200-597 on numpy; ``fit`` is not restated (its parity
+    is "same optimum to tolerance")."""
+
+    def __init__(self, replace=False, impute=True, scale=1.0, scale_tie=False, per=False, per_period=1.0,
+                 per_scale=1.0, per_decay=10.0, input_linear=False, input_linear_scale=100.0, linear=True,
+                 linear_scale=100.0, nonlinear=False, nonlinear_scale=1.0, rq=False, markov=None, noise=0.1,
+                 x_ind=None, normalise_y=True, transform_y=(lambda x: x, lambda x: x)):
+        self.replace = replace
+        self.impute = impute
+        self.sparse = x_ind is not None
+        self.x_ind = None if x_ind is None else _uprank(x_ind)
+        self.model_config = dict(scale=scale, scale_tie=scale_tie, per=per, per_period=per_period,
+                                 per_scale=per_scale, per_decay=per_decay, input_linear=input_linear,
+                                 input_linear_scale=input_linear_scale, linear=linear, linear_scale=linear_scale,
+                                 nonlinear=nonlinear, nonlinear_scale=nonlinear_scale, rq=rq, markov=markov,
+                                 noise=noise)
+        self.vs = _Vars()
+        self.is_conditioned = False
+        self.x = self.y = self.w = None
+        self.n = self.m = self.p = None
+        self.normalise_y = normalise_y
+        self._unnormalise_y, self._normalise_y = (lambda x: x), (lambda x: x)
+        self._transform_y, self._untransform_y = transform_y
+
+    def get_variables(self):
+        return {k: np.array(v) for k, v in self.vs.values.items()}
+
+    def _construct_gpar(self, m, p):
+        """regression.py:185-190 (+ :72-182)."""
+        gpar = GPAR(replace=self.replace, impute=self.impute, x_ind=self.x_ind)
+        for pi in range(p):
+            def model(pi=pi):
+                terms, noise = model_terms(self.vs, m, pi, **self.model_config)
+                return GP(terms), noise
+            gpar = gpar.add_layer(model)
+        return gpar
+
+    def condition(self, x, y, w=None):
+        """regression.py:339-389.  std is the population std (ddof=0) [UNPINNED]."""
+        self.x = _uprank(x)
+        self.y = self._transform_y(_uprank(y))
+        self.w = np.ones_like(self.y) if w is None else _uprank(w)
+        self.n, self.m = self.x.shape
+        self.p = self.y.shape[1]
+        if self.normalise_y:
+            means, stds = [], []
+            for i in range(self.p):
+                y_i = self.y[~np.isnan(self.y[:, i]), i]
+                means.append(np.mean(y_i))
+                std = np.std(y_i)
+                stds.append(std if std > 0 else 1.0)
+            means, stds = np.array(means)[None, :], np.array(stds)[None, :]
+            self._normalise_y = lambda y_: (y_ - means) / stds
+            self._unnormalise_y = lambda y_: y_ * stds + means
+            self.y = self._normalise_y(self.y)
+        self.is_conditioned = True
+
+    def logpdf(self, x, y, w=None, sample_missing=False, posterior=False, normals=None):
+        """regression.py:461-506 (quirk Q1: *un*-normalise is applied to y)."""
+        x = _uprank(x)
+        y = self._unnormalise_y(self._transform_y(_uprank(y)))
+        w = np.ones_like(y) if w is None else _uprank(w)
+        m, p = x.shape[1], y.shape[1]
+        if posterior and not self.is_conditioned:
+            raise RuntimeError("Must condition or fit model before computing the logpdf under the posterior.")
+        gpar = self._construct_gpar(m, p)
+        if posterior:
+            gpar = gpar | (self.x, self.y, self.w)
+        return gpar.logpdf(x, y, w, only_last_layer=False, sample_missing=sample_missing, normals=normals)
+
+    def sample(self, x, w=None, p=None, posterior=False, num_samples=1, latent=False, normals=None):
+        """regression.py:508-564."""
+        x = _uprank(x)
+        if posterior and not self.is_conditioned:
+            raise RuntimeError("Must condition or fit model before sampling from the posterior.")
+        elif not posterior and p is None:
+            raise ValueError("Must specify number of outputs to sample.")
+        if w is None:
+            w = np.ones((x.shape[0], self.p if posterior else p))
+        else:
+            w = _uprank(w)
+        if posterior:
+            gpar = self._construct_gpar(self.m, self.p)
+            gpar = gpar | (self.x, self.y, self.w)
+        else:
+            gpar = self._construct_gpar(x.shape[1], p)
+        normals = Normals() if normals is None else normals
+        samples = []
+        for _ in range(num_samples):
+            samples.append(self._untransform_y(self._unnormalise_y(gpar.sample(x, w, latent=latent, normals=normals))))
+        return samples[0] if num_samples == 1 else samples
+
+    def predict(self, x, w=None, num_samples=100, latent=False, credible_bounds=False, normals=None):
+        """regression.py:566-597."""
+        samples = self.sample(x, w, num_samples=num_samples, latent=latent, posterior=True, normals=normals)
+        if num_samples == 1:
+            samples = [samples]
+        mean = np.mean(samples, axis=0)
+        if credible_bounds:
+            lowers = np.percentile(samples, 2.5, axis=0)
+            uppers = np.percentile(samples, 100 - 2.5, axis=0)
+            return mean, lowers, uppers
+        return mean
