@@ -1,0 +1,283 @@
+// K1: Gram matrix of the GPAR kernel family (feature-map normal form), and the fused
+// cross-covariance x vector product.  HBM-bound on the n^2 * 8 B output; the input rows are
+// staged with the bulk-copy (TMA) engine, features (scaling, sin/cos maps) are built once per
+// tile in shared memory, and each thread produces a 4x4 register block of kernel values.
+#include "common.cuh"
+
+namespace gpar {
+
+constexpr int GT = 64;  // Gram tile edge
+
+__device__ __forceinline__ void stage_rows(double* raw, const double* src, int64_t ld, int rows, uint64_t* bar,
+                                           uint32_t& parity) {
+  // rows x ld doubles, contiguous in global memory.
+  uint32_t bytes = static_cast<uint32_t>(rows * ld * 8);
+  bool bulk_ok = (bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && bytes > 0;
+  if (bulk_ok) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, bytes);
+      tma_bulk_g2s(raw, src, bytes, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+  } else {
+    for (int i = threadIdx.x; i < rows * ld; i += blockDim.x) raw[i] = src[i];
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void build_features(const gpar_kernel_spec_t& spec, double* feat, const double* raw,
+                                               int64_t ld, int rows) {
+  int F = spec.n_feats;
+  for (int i = threadIdx.x; i < F * GT; i += blockDim.x) {
+    int f = i / GT, r = i % GT;
+    feat[i] = (r < rows) ? eval_feature(spec, f, raw + r * ld) : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gram_kernel(const __grid_constant__ gpar_kernel_spec_t spec, const double* __restrict__ X, int64_t ldx, int64_t nx,
+            const double* __restrict__ Y, int64_t ldy, int64_t ny, const double* __restrict__ diag_add, double eps,
+            int sym, int lower_only, double* __restrict__ out, int64_t ldo, int64_t strideX, int64_t strideY,
+            int64_t strideD, int64_t strideO) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (sym && lower_only && bj > bi) return;
+  X += (int64_t)blockIdx.z * strideX;
+  Y += (int64_t)blockIdx.z * strideY;
+  out += (int64_t)blockIdx.z * strideO;
+  if (diag_add) diag_add += (int64_t)blockIdx.z * strideD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int F = spec.n_feats;
+  // layout: [bar (16 B)] [raw_x GT*ldx] [raw_y GT*ldy] [fx F*GT] [fy F*GT]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* raw_x = reinterpret_cast<double*>(smem_raw + 16);
+  double* raw_y = raw_x + GT * ldx;
+  double* fx = raw_y + GT * ldy;
+  double* fy = fx + F * GT;
+
+  const int rows_x = static_cast<int>(min64(GT, nx - (int64_t)bi * GT));
+  const int rows_y = static_cast<int>(min64(GT, ny - (int64_t)bj * GT));
+  const bool diag_tile = sym && (bi == bj);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  stage_rows(raw_x, X + (int64_t)bi * GT * ldx, ldx, rows_x, bar, parity);
+  if (!diag_tile) stage_rows(raw_y, Y + (int64_t)bj * GT * ldy, ldy, rows_y, bar, parity);
+  build_features(spec, fx, raw_x, ldx, rows_x);
+  if (!diag_tile) build_features(spec, fy, raw_y, ldy, rows_y);
+  __syncthreads();
+  const double* fyy = diag_tile ? fx : fy;
+
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double val[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) val[r][c] = 0.0;
+
+  for (int t = 0; t < spec.n_terms; ++t) {
+    const int type = spec.terms[t].type;
+    const double var = spec.terms[t].variance;
+    if (type == GPAR_TERM_CONST) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) val[r][c] += var;
+      continue;
+    }
+    double acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+    const int f0 = spec.terms[t].f_begin, f1 = spec.terms[t].f_end;
+    if (type == GPAR_TERM_LINEAR) {
+      for (int f = f0; f < f1; ++f) {
+        double xv[4], yv[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xv[r] = fx[f * GT + ty + 16 * r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) yv[c] = fyy[f * GT + tx + 16 * c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = fma(xv[r], yv[c], acc[r][c]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) val[r][c] = fma(var, acc[r][c], val[r][c]);
+    } else {
+      for (int f = f0; f < f1; ++f) {
+        double xv[4], yv[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xv[r] = fx[f * GT + ty + 16 * r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) yv[c] = fyy[f * GT + tx + 16 * c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            double d = xv[r] - yv[c];
+            acc[r][c] = fma(d, d, acc[r][c]);
+          }
+      }
+      if (type == GPAR_TERM_EQ) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) val[r][c] = fma(var, exp(-0.5 * acc[r][c]), val[r][c]);
+      } else {
+        const double alpha = spec.terms[t].alpha;
+        const double inv2a = 1.0 / (2.0 * alpha);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) val[r][c] = fma(var, pow(fma(acc[r][c], inv2a, 1.0), -alpha), val[r][c]);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int lr = ty + 16 * r;
+    if (lr >= rows_x) continue;
+    const int64_t gr = (int64_t)bi * GT + lr;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int lc = tx + 16 * c;
+      if (lc >= rows_y) continue;
+      const int64_t gc = (int64_t)bj * GT + lc;
+      double v = val[r][c];
+      if (sym && gr == gc) v += (diag_add ? diag_add[gr] : 0.0) + eps;
+      out[gr * ldo + gc] = v;
+    }
+  }
+}
+
+// out[j] = sum_i k(Xq[j], Xa[i]) v[i].  One CTA per QT query rows; the a-rows stream through
+// shared memory in chunks of 256 (features built cooperatively).
+constexpr int QT = 8;
+constexpr int AC = 256;
+
+__global__ void __launch_bounds__(AC)
+gram_gemv_kernel(const __grid_constant__ gpar_kernel_spec_t spec, const double* __restrict__ Xq, int64_t ldq,
+                 int64_t nq, const double* __restrict__ Xa, int64_t lda, int64_t na, const double* __restrict__ v,
+                 double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int F = spec.n_feats;
+  double* fq = reinterpret_cast<double*>(smem_raw);  // [F][QT]
+  double* fa = fq + F * QT;                           // [F][AC]
+  double* red = fa + F * AC;                          // [32]
+  const int64_t q0 = (int64_t)blockIdx.x * QT;
+  const int nqt = static_cast<int>(min64(QT, nq - q0));
+  for (int i = threadIdx.x; i < F * QT; i += blockDim.x) {
+    int f = i / QT, r = i % QT;
+    fq[i] = (r < nqt) ? eval_feature(spec, f, Xq + (q0 + r) * ldq) : 0.0;
+  }
+  double sums[QT];
+#pragma unroll
+  for (int q = 0; q < QT; ++q) sums[q] = 0.0;
+  for (int64_t a0 = 0; a0 < na; a0 += AC) {
+    __syncthreads();
+    const int64_t ia = a0 + threadIdx.x;
+    const bool live = ia < na;
+    for (int f = 0; f < F; ++f) fa[f * AC + threadIdx.x] = live ? eval_feature(spec, f, Xa + ia * lda) : 0.0;
+    __syncthreads();
+    if (live) {
+      const double vi = v[ia];
+#pragma unroll
+      for (int q = 0; q < QT; ++q) {
+        double val = 0.0;
+        for (int t = 0; t < spec.n_terms; ++t) {
+          const gpar_term_t& T = spec.terms[t];
+          if (T.type == GPAR_TERM_CONST) {
+            val += T.variance;
+            continue;
+          }
+          double acc = 0.0;
+          if (T.type == GPAR_TERM_LINEAR) {
+            for (int f = T.f_begin; f < T.f_end; ++f) acc = fma(fq[f * QT + q], fa[f * AC + threadIdx.x], acc);
+            val = fma(T.variance, acc, val);
+          } else {
+            for (int f = T.f_begin; f < T.f_end; ++f) {
+              double d = fq[f * QT + q] - fa[f * AC + threadIdx.x];
+              acc = fma(d, d, acc);
+            }
+            if (T.type == GPAR_TERM_EQ)
+              val = fma(T.variance, exp(-0.5 * acc), val);
+            else
+              val = fma(T.variance, pow(fma(acc, 1.0 / (2.0 * T.alpha), 1.0), -T.alpha), val);
+          }
+        }
+        sums[q] = fma(val, vi, sums[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < QT; ++q) {
+    double s = block_sum(sums[q], red);
+    if (threadIdx.x == 0 && q < nqt) out[q0 + q] = s;
+  }
+}
+
+}  // namespace gpar
+
+using namespace gpar;
+
+extern "C" int gpar_gram_batched(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t nx,
+                                 int64_t strideX, const double* Y, int64_t ldy, int64_t ny, int64_t strideY,
+                                 const double* diag_add, int64_t strideD, double eps, int lower_only, double* out,
+                                 int64_t ldo, int64_t strideO, int64_t batch, void* stream) {
+  if (!spec || spec->n_feats < 0 || spec->n_feats > GPAR_MAX_FEATS || spec->n_terms < 0 ||
+      spec->n_terms > GPAR_MAX_TERMS) {
+    set_error("gpar_gram: bad spec");
+    return -1;
+  }
+  if (!X || ldx <= 0) { set_error("gpar_gram: bad X"); return -2; }
+  if (nx < 0) return -4;
+  const int sym = (Y == nullptr);
+  if (sym) { Y = X; ldy = ldx; ny = nx; strideY = strideX; }
+  if (batch <= 0) return 0;
+  if (batch > 65535) { set_error("gpar_gram: batch > 65535"); return -17; }
+  if (ny < 0) return -7;
+  if (!out || ldo < ny) { set_error("gpar_gram: bad out/ldo"); return -11; }
+  if (nx == 0 || ny == 0) return 0;
+  size_t smem = 16 + sizeof(double) * (size_t)(GT * ldx + GT * ldy + 2 * (size_t)spec->n_feats * GT);
+  if (smem > 227 * 1024) { set_error("gpar_gram: ldx/ldy/features too large for shared memory (%zu B)", smem); return -3; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((ny + GT - 1) / GT), (unsigned)((nx + GT - 1) / GT), (unsigned)batch);
+  gram_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(*spec, X, ldx, nx, Y, ldy, ny, diag_add, eps, sym,
+                                                         lower_only, out, ldo, strideX, strideY, strideD, strideO);
+  return check_launch("gpar_gram");
+}
+
+extern "C" int gpar_gram(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t nx, const double* Y,
+                         int64_t ldy, int64_t ny, const double* diag_add, double eps, int lower_only, double* out,
+                         int64_t ldo, void* stream) {
+  return gpar_gram_batched(spec, X, ldx, nx, 0, Y, ldy, ny, 0, diag_add, 0, eps, lower_only, out, ldo, 0, 1, stream);
+}
+
+extern "C" int gpar_gram_gemv(const gpar_kernel_spec_t* spec, const double* Xq, int64_t ldq, int64_t nq,
+                              const double* Xa, int64_t lda, int64_t na, const double* v, double* out, void* stream) {
+  if (!spec || spec->n_feats > GPAR_MAX_FEATS || spec->n_terms > GPAR_MAX_TERMS) { set_error("gpar_gram_gemv: bad spec"); return -1; }
+  if (nq <= 0) return 0;
+  size_t smem = sizeof(double) * ((size_t)spec->n_feats * (QT + AC) + 32);
+  if (smem > 227 * 1024) { set_error("gpar_gram_gemv: too many features"); return -1; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gram_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  unsigned grid = (unsigned)((nq + QT - 1) / QT);
+  gram_gemv_kernel<<<grid, AC, smem, (cudaStream_t)stream>>>(*spec, Xq, ldq, nq, Xa, lda, na, v, out);
+  return check_launch("gpar_gram_gemv");
+}

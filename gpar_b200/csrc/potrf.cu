@@ -1,0 +1,445 @@
+// K2 / K4 / K5: blocked Cholesky with appended row blocks, triangular solve of row blocks, and
+// the symmetric rank-k downdate -- all on the DMMA GEMM core (gemm_core.cuh).
+//
+// Right-looking tile algorithm, tile = 128:
+//   for k:  diag  : L_kk = chol(A_kk) and Linv_kk = L_kk^-1 (one CTA, latency bound: warp-level
+//                   32x32 factor with shuffle pivots + DMMA block updates out of shared memory)
+//           panel : A_ik <- A_ik Linv_kk^T          (NT GEMM, K = 128)
+//           update: A_ij <- A_ij - A_ik A_jk^T      (NT GEMM, K = 128, lower tiles only)
+// Appended rows B (nb x n) ride along as extra row tiles, so B <- B L^-T falls out of the same
+// sweep: with B = y^T this is the forward solve of the log-marginal; with the joint matrix
+// [[K_aa, .], [K_*a, K_**]] the sweep yields L, V^T = K_*a L^-T and chol(K_** - V^T V) at once.
+#include "gemm_core.cuh"
+
+namespace gpar {
+
+// --------------------------------------------------------------------------------------
+// Diagonal tile: factor + invert, entirely in shared memory.
+// --------------------------------------------------------------------------------------
+constexpr int DLD = 129;  // row stride of the tile in shared memory
+constexpr int ILD = 33;   // row stride of a 32x32 inverse block
+constexpr int NB32 = TILE / 32;
+constexpr int NINV = NB32 * (NB32 + 1) / 2;  // 10 lower blocks
+constexpr size_t DIAG_SMEM_BYTES = sizeof(double) * (TILE * DLD + NINV * 32 * ILD + TILE) + 16;
+
+__device__ __forceinline__ int blk(int b, int a) { return b * (b + 1) / 2 + a; }
+
+// Warp-level Cholesky of the 32x32 block at Ls (row stride DLD).  Lane r owns row r in
+// registers; finished rows are broadcast through shared memory.  Returns the 1-based index of
+// the first non-positive pivot (0 if none) in every lane.
+__device__ __forceinline__ int potf2_32(double* Ls, double* rdiag, int lane) {
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? Ls[lane * DLD + c] : 0.0;
+  int bad = 0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int t = 0; t + 3 < c; t += 4) {
+      s0 = fma(a[t], Ls[c * DLD + t], s0);
+      s1 = fma(a[t + 1], Ls[c * DLD + t + 1], s1);
+      s2 = fma(a[t + 2], Ls[c * DLD + t + 2], s2);
+      s3 = fma(a[t + 3], Ls[c * DLD + t + 3], s3);
+    }
+#pragma unroll
+    for (int t = (c / 4) * 4; t < c; ++t) s0 = fma(a[t], Ls[c * DLD + t], s0);
+    const double v = a[c] - ((s0 + s1) + (s2 + s3));
+    double piv = __shfl_sync(0xffffffffu, v, c);
+    if (!(piv > 0.0)) {
+      if (bad == 0) bad = c + 1;
+      piv = 1.0;
+    }
+    const double rs = rsqrt(piv);
+    const double l = (lane == c) ? piv * rs : v * rs;
+    a[c] = l;
+    if (lane >= c) Ls[lane * DLD + c] = l;
+    if (lane == c) rdiag[c] = rs;
+    __syncwarp();
+  }
+  return bad;
+}
+
+// Warp-level inverse of the lower-triangular 32x32 block at Ls: lane j solves L x = e_j.
+__device__ __forceinline__ void trtri_32(const double* Ls, const double* rdiag, double* inv, int lane) {
+  double x[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 3 < i; k += 4) {
+      s0 = fma(-Ls[i * DLD + k], x[k], s0);
+      s1 = fma(-Ls[i * DLD + k + 1], x[k + 1], s1);
+      s2 = fma(-Ls[i * DLD + k + 2], x[k + 2], s2);
+      s3 = fma(-Ls[i * DLD + k + 3], x[k + 3], s3);
+    }
+#pragma unroll
+    for (int k = (i / 4) * 4; k < i; ++k) s0 = fma(-Ls[i * DLD + k], x[k], s0);
+    x[i] = ((s0 + s1) + (s2 + s3)) * rdiag[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) inv[i * ILD + lane] = x[i];
+}
+
+// acc[t] += sum_k A(gid, k0+tig) * B(k0+tig, t*8+gid) over K (multiple of 4): one 8 x (8*NTN) strip.
+template <int NTN, class FA, class FB>
+__device__ __forceinline__ void strip_mma(double (&c)[NTN][2], int K, FA a, FB b, int gid, int tig) {
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    const double av = a(gid, k0 + tig);
+#pragma unroll
+    for (int t = 0; t < NTN; ++t) {
+      const double bv = b(k0 + tig, t * 8 + gid);
+      dmma884(c[t][0], c[t][1], av, bv);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, int64_t n, double* __restrict__ ws,
+                  int64_t strideWs, int32_t* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Ls = reinterpret_cast<double*>(smem_raw);
+  double* Inv = Ls + TILE * DLD;
+  double* rdiag = Inv + NINV * 32 * ILD;
+  int* s_bad = reinterpret_cast<int*>(rdiag + TILE);
+
+  const int b = blockIdx.x;
+  A += (int64_t)b * strideA;
+  ws += (int64_t)b * strideWs + (int64_t)kt * TILE * TILE;
+  const int64_t j0 = (int64_t)kt * TILE;
+  const int kb = static_cast<int>(min64(TILE, n - j0));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+
+  for (int idx = tid; idx < TILE * TILE; idx += 256) {
+    const int r = idx >> 7, c = idx & 127;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < kb && c <= r) v = A[(j0 + r) * lda + j0 + c];
+    Ls[r * DLD + c] = v;
+  }
+  if (tid == 0) *s_bad = 0;
+  __syncthreads();
+
+  for (int a = 0; a < NB32; ++a) {
+    const int o = 32 * a;
+    if (warp == 0) {
+      int bad = potf2_32(Ls + o * DLD + o, rdiag + o, lane);
+      if (bad && lane == 0 && *s_bad == 0) *s_bad = o + bad;
+      __syncwarp();
+      trtri_32(Ls + o * DLD + o, rdiag + o, Inv + blk(a, a) * 32 * ILD, lane);
+    }
+    __syncthreads();
+    const int rem = TILE - (o + 32);
+    if (rem == 0) break;
+    // panel: X = T inv_aa^T, T = rows [o+32, 128) x cols [o, o+32)   (in place, warp owns whole rows)
+    {
+      const double* inv = Inv + blk(a, a) * 32 * ILD;
+      for (int strip = warp; strip < rem / 8; strip += 8) {
+        double* T = Ls + (o + 32 + strip * 8) * DLD + o;
+        double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        strip_mma<4>(
+            c, 32, [&](int m, int k) { return T[m * DLD + k]; }, [&](int k, int nn) { return inv[nn * ILD + k]; }, gid,
+            tig);
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          T[gid * DLD + t * 8 + 2 * tig] = c[t][0];
+          T[gid * DLD + t * 8 + 2 * tig + 1] = c[t][1];
+        }
+      }
+    }
+    __syncthreads();
+    // trailing: T2[m][nn] -= sum_k X[m][k] X[nn][k], lower 8x8 tiles only
+    {
+      const double* X = Ls + (o + 32) * DLD + o;
+      double* T2 = Ls + (o + 32) * DLD + (o + 32);
+      const int ntm = rem / 8;
+      // work units: (tm, group g of 4 column tiles) with 4*g <= tm
+      int unit = 0;
+      for (int tm = 0; tm < ntm; ++tm) {
+        for (int g = 0; g * 4 <= tm; ++g, ++unit) {
+          if ((unit & 7) != warp) continue;
+          double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+          const double* Xa = X + (tm * 8) * DLD;
+          const double* Xb = X + (g * 32) * DLD;
+          strip_mma<4>(
+              c, 32, [&](int m, int k) { return Xa[m * DLD + k]; }, [&](int k, int nn) { return Xb[nn * DLD + k]; },
+              gid, tig);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int col = g * 32 + t * 8 + 2 * tig;
+            if (g * 4 + t <= tm) {
+              double* p = T2 + (tm * 8 + gid) * DLD + col;
+              p[0] -= c[t][0];
+              p[1] -= c[t][1];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- assemble the off-diagonal blocks of the inverse, block row by block row --------------
+  for (int bb = 1; bb < NB32; ++bb) {
+    // stage 1: M_ba = sum_{c=a}^{bb-1} L[bb][c] Inv[c][a]  -> stored in Inv[bb][a]
+    for (int unit = warp; unit < bb * 4; unit += 8) {
+      const int a = unit >> 2, tm = unit & 3;
+      double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+      for (int cc = a; cc < bb; ++cc) {
+        const double* Lb = Ls + (32 * bb + tm * 8) * DLD + 32 * cc;
+        const double* Ic = Inv + blk(cc, a) * 32 * ILD;
+        strip_mma<4>(
+            c, 32, [&](int m, int k) { return Lb[m * DLD + k]; }, [&](int k, int nn) { return Ic[k * ILD + nn]; }, gid,
+            tig);
+      }
+      double* M = Inv + blk(bb, a) * 32 * ILD + (tm * 8) * ILD;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        M[gid * ILD + t * 8 + 2 * tig] = c[t][0];
+        M[gid * ILD + t * 8 + 2 * tig + 1] = c[t][1];
+      }
+    }
+    __syncthreads();
+    // stage 2: Inv[bb][a] = -Inv[bb][bb] M_ba, in place: a warp owns 8 whole columns.
+    for (int unit = warp; unit < bb * 4; unit += 8) {
+      const int a = unit >> 2, tn = unit & 3;
+      double* M = Inv + blk(bb, a) * 32 * ILD + tn * 8;
+      const double* Ib = Inv + blk(bb, bb) * 32 * ILD;
+      double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+      // out[m][nn] over 4 row tiles: treat row tiles as the "N" strips by transposing roles:
+      // out^T[nn][m] = sum_k M^T[nn][k] Ib^T[k][m]  -> A(nn,k) = M[k][nn], B(k,m) = Ib[m][k]
+      strip_mma<4>(
+          c, 32, [&](int nn, int k) { return M[k * ILD + nn]; }, [&](int k, int m) { return Ib[m * ILD + k]; }, gid,
+          tig);
+      __syncwarp();
+      // c[t][e] = out^T[gid][t*8 + 2*tig + e] = out[m = t*8+2*tig+e][nn = gid]
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        M[(t * 8 + 2 * tig) * ILD + gid] = -c[t][0];
+        M[(t * 8 + 2 * tig + 1) * ILD + gid] = -c[t][1];
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write back L (lower part of the valid block) and Linv (dense 128x128, zero padded) -----
+  for (int idx = tid; idx < TILE * TILE; idx += 256) {
+    const int r = idx >> 7, c = idx & 127;
+    if (r < kb && c <= r) A[(j0 + r) * lda + j0 + c] = Ls[r * DLD + c];
+    double v = 0.0;
+    if (r < kb && c <= r) v = Inv[blk(r >> 5, c >> 5) * 32 * ILD + (r & 31) * ILD + (c & 31)];
+    ws[idx] = v;
+  }
+  if (tid == 0 && *s_bad != 0 && info[b] == 0) info[b] = static_cast<int32_t>(j0) + *s_bad;
+}
+
+// --------------------------------------------------------------------------------------
+// T (rows x kb) <- T Linv^T for every 128-row tile of a row block.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+trsm_tile_kernel(double* __restrict__ T1, int64_t ldt1, int64_t rows1, int64_t strideT1, int nt1,
+                 double* __restrict__ T2, int64_t ldt2, int64_t rows2, int64_t strideT2, int kb,
+                 const double* __restrict__ Linv, int64_t strideW) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
+  int ti = blockIdx.x;
+  const int b = blockIdx.y;
+  double* T;
+  int64_t ldt, rows;
+  if (ti < nt1) {
+    T = T1 + (int64_t)b * strideT1; ldt = ldt1; rows = rows1;
+  } else {
+    ti -= nt1;
+    T = T2 + (int64_t)b * strideT2; ldt = ldt2; rows = rows2;
+  }
+  T += (int64_t)ti * TILE * ldt;
+  Linv += (int64_t)b * strideW;
+  const int valid = static_cast<int>(min64(TILE, rows - (int64_t)ti * TILE));
+  Acc acc;
+  acc_zero(acc);
+  gemm_nt_mainloop(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);
+  store_tile<0>(T, ldt, valid, kb, acc, false);
+}
+
+// --------------------------------------------------------------------------------------
+// C(ti, tj) -= Aop(ti) Bop(tj)^T, K columns.  lower != 0: only tiles tj <= ti, and only
+// col <= row on the diagonal tiles.
+// --------------------------------------------------------------------------------------
+struct SubArgs {
+  // primary row space (row tiles [0, nt_rows1)): symmetric/lower part when lower != 0
+  double* C; int64_t ldc; int64_t c_rows; int64_t c_cols; int64_t strideC;
+  const double* Aop; int64_t lda; int64_t strideA;
+  const double* Bop; int64_t ldb; int64_t strideB;
+  int K; int lower; int nt_rows1;
+  // secondary row space (appended rows, row tiles >= nt_rows1): all column tiles
+  double* C2; int64_t ldc2; int64_t c_rows2; int64_t strideC2;
+  const double* Aop2; int64_t lda2; int64_t strideA2;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_sub_kernel(const SubArgs p) {
+  const int tj = blockIdx.x, b = blockIdx.z;
+  int ti = blockIdx.y;
+  const bool second = ti >= p.nt_rows1;
+  if (!second && p.lower && tj > ti) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
+  const int cols = static_cast<int>(min64(TILE, p.c_cols - (int64_t)tj * TILE));
+  const double* Bp = p.Bop + (int64_t)b * p.strideB + (int64_t)tj * TILE * p.ldb;
+  const double* Ap;
+  double* C;
+  int64_t lda, ldc;
+  int rows;
+  bool lower_diag = false;
+  if (!second) {
+    rows = static_cast<int>(min64(TILE, p.c_rows - (int64_t)ti * TILE));
+    lda = p.lda; ldc = p.ldc;
+    Ap = p.Aop + (int64_t)b * p.strideA + (int64_t)ti * TILE * lda;
+    C = p.C + (int64_t)b * p.strideC + (int64_t)ti * TILE * ldc + (int64_t)tj * TILE;
+    lower_diag = p.lower && ti == tj;
+  } else {
+    ti -= p.nt_rows1;
+    rows = static_cast<int>(min64(TILE, p.c_rows2 - (int64_t)ti * TILE));
+    lda = p.lda2; ldc = p.ldc2;
+    Ap = p.Aop2 + (int64_t)b * p.strideA2 + (int64_t)ti * TILE * lda;
+    C = p.C2 + (int64_t)b * p.strideC2 + (int64_t)ti * TILE * ldc + (int64_t)tj * TILE;
+  }
+  Acc acc;
+  acc_zero(acc);
+  gemm_nt_mainloop(stages, Ap, lda, rows, Bp, p.ldb, cols, p.K, acc);
+  store_tile<1>(C, ldc, rows, cols, acc, lower_diag);
+}
+
+// --------------------------------------------------------------------------------------
+// B (nb x n) <- B L^-T with L already factored: every CTA owns one 128-row tile of B and sweeps
+// the column tiles left to right (left-looking), so no inter-CTA dependency exists.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+trsm_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const double* __restrict__ ws,
+                 double* __restrict__ B, int64_t ldb, int64_t nb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
+  const int ti = blockIdx.x;
+  double* Brow = B + (int64_t)ti * TILE * ldb;
+  const int valid = static_cast<int>(min64(TILE, nb - (int64_t)ti * TILE));
+  const int nt = static_cast<int>((n + TILE - 1) / TILE);
+  for (int j = 0; j < nt; ++j) {
+    const int kb = static_cast<int>(min64(TILE, n - (int64_t)j * TILE));
+    Acc acc;
+    if (j > 0) {
+      acc_zero(acc);
+      gemm_nt_mainloop(stages, Brow, ldb, valid, L + (int64_t)j * TILE * ldl, ldl, kb, j * TILE, acc);
+      store_tile<1>(Brow + (int64_t)j * TILE, ldb, valid, kb, acc, false);
+      __threadfence();
+      __syncthreads();
+    }
+    acc_zero(acc);
+    gemm_nt_mainloop(stages, Brow + (int64_t)j * TILE, ldb, valid, ws + (int64_t)j * TILE * TILE, TILE, kb, kb, acc);
+    store_tile<0>(Brow + (int64_t)j * TILE, ldb, valid, kb, acc, false);
+    __threadfence();
+    __syncthreads();
+  }
+}
+
+static void set_smem_attrs() {
+  static bool done = false;
+  if (done) return;
+  cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM_BYTES);
+  cudaFuncSetAttribute(trsm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
+  cudaFuncSetAttribute(gemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
+  cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
+  done = true;
+}
+
+}  // namespace gpar
+
+using namespace gpar;
+
+extern "C" size_t gpar_potrf_workspace_bytes(int64_t n, int64_t batch) {
+  if (n <= 0 || batch <= 0) return 0;
+  int64_t nt = (n + TILE - 1) / TILE;
+  return (size_t)batch * (size_t)nt * TILE * TILE * sizeof(double);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, double* B, int64_t ldb, int64_t nb,
+                          int64_t strideB, int64_t batch, double* ws, int32_t* info, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!A || !aligned16(A)) { set_error("gpar_potrf: A null or not 16-byte aligned"); return -1; }
+  if (lda < n || (lda & 1)) { set_error("gpar_potrf: lda must be even and >= n"); return -2; }
+  if (n < 0) return -3;
+  if (batch > 1 && (strideA & 1)) { set_error("gpar_potrf: strideA must be even"); return -4; }
+  if (nb > 0 && (!B || !aligned16(B) || ldb < n || (ldb & 1) || (batch > 1 && (strideB & 1)))) {
+    set_error("gpar_potrf: bad appended row block");
+    return -5;
+  }
+  if (batch <= 0) return -9;
+  if (!ws || !aligned16(ws)) { set_error("gpar_potrf: bad workspace"); return -10; }
+  if (!info) return -11;
+  if (batch > 65535) { set_error("gpar_potrf: batch > 65535"); return -9; }
+  set_smem_attrs();
+  cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, stream);
+  if (n == 0) return 0;
+  const int nt = (int)((n + TILE - 1) / TILE);
+  const int64_t strideWs = (int64_t)nt * TILE * TILE;
+  const int nbt = (int)((nb + TILE - 1) / TILE);
+  for (int k = 0; k < nt; ++k) {
+    const int64_t j0 = (int64_t)k * TILE;
+    const int kb = (int)((n - j0 < TILE) ? (n - j0) : TILE);
+    potrf_diag_kernel<<<(unsigned)batch, 256, DIAG_SMEM_BYTES, stream>>>(A, lda, strideA, k, n, ws, strideWs, info);
+    const int64_t below = n - (j0 + TILE);
+    const double* Linv = ws + (int64_t)k * TILE * TILE;
+    const int ntr = below > 0 ? (int)((below + TILE - 1) / TILE) : 0;
+    if (ntr + nbt > 0) {
+      dim3 g((unsigned)(ntr + nbt), (unsigned)batch);
+      trsm_tile_kernel<<<g, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(
+          below > 0 ? A + (j0 + TILE) * lda + j0 : A, lda, below > 0 ? below : 0, strideA, ntr,
+          nb > 0 ? B + j0 : B, ldb, nb, strideB, kb, Linv, strideWs);
+    }
+    if (below > 0) {
+      SubArgs p;
+      p.C = A + (j0 + TILE) * lda + (j0 + TILE); p.ldc = lda; p.c_rows = below; p.c_cols = below; p.strideC = strideA;
+      p.Aop = A + (j0 + TILE) * lda + j0; p.lda = lda; p.strideA = strideA;
+      p.Bop = p.Aop; p.ldb = lda; p.strideB = strideA;
+      p.K = kb; p.lower = 1; p.nt_rows1 = ntr;
+      p.C2 = nb > 0 ? B + (j0 + TILE) : nullptr; p.ldc2 = ldb; p.c_rows2 = nb; p.strideC2 = strideB;
+      p.Aop2 = nb > 0 ? B + j0 : nullptr; p.lda2 = ldb; p.strideA2 = strideB;
+      gemm_sub_kernel<<<dim3((unsigned)ntr, (unsigned)(ntr + nbt), (unsigned)batch), GEMM_THREADS, GEMM_SMEM_BYTES,
+                        stream>>>(p);
+    }
+  }
+  return check_launch("gpar_potrf");
+}
+
+extern "C" int gpar_trsm_rows(const double* L, int64_t ldl, int64_t n, const double* ws, double* B, int64_t ldb,
+                              int64_t nb, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!L || !aligned16(L) || (ldl & 1) || ldl < n) { set_error("gpar_trsm_rows: bad L"); return -1; }
+  if (!ws || !aligned16(ws)) return -4;
+  if (nb <= 0 || n <= 0) return 0;
+  if (!B || !aligned16(B) || (ldb & 1) || ldb < n) { set_error("gpar_trsm_rows: bad B"); return -5; }
+  set_smem_attrs();
+  unsigned g = (unsigned)((nb + TILE - 1) / TILE);
+  trsm_rows_kernel<<<g, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(L, ldl, n, ws, B, ldb, nb);
+  return check_launch("gpar_trsm_rows");
+}
+
+extern "C" int gpar_syrk_sub(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw,
+                             int64_t k, int64_t strideW, int64_t batch, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!C || !aligned16(C) || (ldc & 1) || ldc < n) { set_error("gpar_syrk_sub: bad C"); return -1; }
+  if (!W || !aligned16(W) || (ldw & 1) || ldw < k) { set_error("gpar_syrk_sub: bad W"); return -5; }
+  if (batch > 1 && ((strideC & 1) || (strideW & 1))) { set_error("gpar_syrk_sub: odd batch stride"); return -4; }
+  if (n <= 0 || k <= 0 || batch <= 0) return 0;
+  if (batch > 65535) { set_error("gpar_syrk_sub: batch > 65535"); return -9; }
+  set_smem_attrs();
+  const unsigned nt = (unsigned)((n + TILE - 1) / TILE);
+  SubArgs p;
+  p.C = C; p.ldc = ldc; p.c_rows = n; p.c_cols = n; p.strideC = strideC;
+  p.Aop = W; p.lda = ldw; p.strideA = strideW;
+  p.Bop = W; p.ldb = ldw; p.strideB = strideW;
+  p.K = (int)k; p.lower = 1; p.nt_rows1 = (int)nt;
+  p.C2 = nullptr; p.ldc2 = 0; p.c_rows2 = 0; p.strideC2 = 0; p.Aop2 = nullptr; p.lda2 = 0; p.strideA2 = 0;
+  gemm_sub_kernel<<<dim3(nt, nt, (unsigned)batch), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+  return check_launch("gpar_syrk_sub");
+}

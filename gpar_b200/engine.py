@@ -1,0 +1,230 @@
+"""Device engine: thin Python wrappers over the C ABI plus the ``Factor`` object
+(Cholesky of stacked observation blocks with optional appended test rows) that
+the GPAR host loop in :mod:`gpar_b200.model` drives.
+
+torch is plumbing only (device memory, streams, host<->device copies); every
+arithmetic step on the hot path is one of our sm_100a kernels."""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TILE, check
+
+__all__ = ["Engine", "Factor"]
+
+F64 = torch.float64
+
+
+def _even(n):
+    return n + (n & 1)
+
+
+class Engine:
+    """Owns the library handle, the device and the launch counter."""
+
+    def __init__(self, device=None, epsilon=1e-12):
+        if not torch.cuda.is_available():
+            raise _lib.GparError("gpar_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.epsilon = float(epsilon)
+        self.launches = 0  # kernels of ours launched so far
+        self.flops = 0.0  # algorithmic flops of the dense contractions issued (bookkeeping for bench.py)
+
+    # -- plumbing -----------------------------------------------------------
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, *shape, dtype=F64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=F64):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def to_device(self, a, dtype=F64):
+        t = torch.as_tensor(np.ascontiguousarray(a))
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True)
+
+    @staticmethod
+    def addr(t, offset=0):
+        return C.c_void_p(t.data_ptr() + 8 * int(offset))
+
+    # -- K1 -------------------------------------------------------------------
+    def gram(self, spec, X, ldx, nx, out, ldo, Y=None, ldy=0, ny=0, diag=None, lower_only=True, x_off=0, y_off=0,
+             out_off=0):
+        rc = self.lib.gpar_gram(C.byref(spec), self.addr(X, x_off), ldx, nx, None if Y is None else self.addr(Y, y_off),
+                                ldy, ny, None if diag is None else self.addr(diag), self.epsilon, int(lower_only),
+                                self.addr(out, out_off), ldo, self.stream)
+        check(rc, "gpar_gram")
+        self.launches += 1
+
+    def gram_batched(self, spec, X, ldx, nx, strideX, out, ldo, strideO, batch, diag=None, strideD=0, lower_only=True):
+        rc = self.lib.gpar_gram_batched(C.byref(spec), self.addr(X), ldx, nx, strideX, None, 0, 0, 0,
+                                        None if diag is None else self.addr(diag), strideD, self.epsilon,
+                                        int(lower_only), self.addr(out), ldo, strideO, batch, self.stream)
+        check(rc, "gpar_gram_batched")
+        self.launches += 1
+
+    # -- K2 -------------------------------------------------------------------
+    def potrf(self, A, lda, n, B=None, ldb=0, nb=0, batch=1, strideA=0, strideB=0, a_off=0):
+        nbytes = self.lib.gpar_potrf_workspace_bytes(n, batch)
+        ws = self.empty(max(nbytes // 8, 2))
+        info = torch.zeros(batch, dtype=torch.int32, device=self.device)
+        rc = self.lib.gpar_potrf(self.addr(A, a_off), lda, n, strideA, None if B is None else self.addr(B), ldb, nb,
+                                 strideB, batch, self.addr(ws), C.c_void_p(info.data_ptr()), self.stream)
+        check(rc, "gpar_potrf")
+        nt = (n + TILE - 1) // TILE
+        self.launches += nt + max(nt - 1, 0) + (nt if nb > 0 else max(nt - 1, 0))
+        self.flops += batch * (n ** 3 / 3.0 + nb * float(n) ** 2)
+        return ws, info
+
+    def trsm_rows(self, L, ldl, n, ws, B, ldb, nb):
+        rc = self.lib.gpar_trsm_rows(self.addr(L), ldl, n, self.addr(ws), self.addr(B), ldb, nb, self.stream)
+        check(rc, "gpar_trsm_rows")
+        self.launches += 1
+        self.flops += nb * float(n) ** 2
+
+    def syrk_sub(self, Cm, ldc, n, W, ldw, k, batch=1, strideC=0, strideW=0, c_off=0, w_off=0):
+        rc = self.lib.gpar_syrk_sub(self.addr(Cm, c_off), ldc, n, strideC, self.addr(W, w_off), ldw, k, strideW, batch,
+                                    self.stream)
+        check(rc, "gpar_syrk_sub")
+        self.launches += 1
+        self.flops += batch * float(n) ** 2 * k
+
+    # -- K3 -------------------------------------------------------------------
+    def backsolve(self, L, ldl, n, ws, u):
+        alpha = self.empty(max(n, 1))
+        work = self.empty(max(n, 1))
+        rc = self.lib.gpar_backsolve(self.addr(L), ldl, n, self.addr(ws), self.addr(u), self.addr(alpha),
+                                     self.addr(work), self.stream)
+        check(rc, "gpar_backsolve")
+        self.launches += (n + TILE - 1) // TILE
+        return alpha
+
+    def logdet_quad(self, L, ldl, n, u, out2, l_off=0, u_off=0, out_off=0):
+        rc = self.lib.gpar_logdet_quad(self.addr(L, l_off), ldl, n, None if u is None else self.addr(u, u_off),
+                                       self.addr(out2, out_off), self.stream)
+        check(rc, "gpar_logdet_quad")
+        self.launches += 1
+
+    # -- K6 -------------------------------------------------------------------
+    def gemv(self, A, lda, m, n, x, y, a_off=0):
+        rc = self.lib.gpar_gemv(self.addr(A, a_off), lda, m, n, self.addr(x), self.addr(y), self.stream)
+        check(rc, "gpar_gemv")
+        self.launches += 1 if m > 0 else 0
+
+    def gram_gemv(self, spec, Xq, ldq, nq, Xa, lda, na, v, out):
+        rc = self.lib.gpar_gram_gemv(C.byref(spec), self.addr(Xq), ldq, nq, self.addr(Xa), lda, na, self.addr(v),
+                                     self.addr(out), self.stream)
+        check(rc, "gpar_gram_gemv")
+        self.launches += 1 if nq > 0 else 0
+
+    # -- K7 -------------------------------------------------------------------
+    def sample_affine(self, Cm, ldc, n, Z, out, ns, batch=1, strideC=0, mean=None, sd=None, Z2=None, c_off=0):
+        rc = self.lib.gpar_sample_affine(self.addr(Cm, c_off), ldc, n, strideC, None if mean is None else self.addr(mean),
+                                         None if sd is None else self.addr(sd), self.addr(Z),
+                                         None if Z2 is None else self.addr(Z2), ns, batch, self.addr(out), self.stream)
+        check(rc, "gpar_sample_affine")
+        self.launches += 1
+
+    # -- K9 -------------------------------------------------------------------
+    def gather_rows(self, src, lds, idx, n_out, ncols, dst, ldd, src_off=0, dst_off=0):
+        rc = self.lib.gpar_gather_rows(self.addr(src, src_off), lds, None if idx is None else C.c_void_p(idx.data_ptr()),
+                                       n_out, ncols, self.addr(dst, dst_off), ldd, self.stream)
+        check(rc, "gpar_gather_rows")
+        self.launches += 1 if n_out * ncols > 0 else 0
+
+    def scatter_col(self, dst, ldd, col, idx, src, n, src_off=0):
+        rc = self.lib.gpar_scatter_col(self.addr(dst), ldd, col, None if idx is None else C.c_void_p(idx.data_ptr()),
+                                       self.addr(src, src_off), n, self.stream)
+        check(rc, "gpar_scatter_col")
+        self.launches += 1 if n > 0 else 0
+
+    def mean_identity(self, y, d, alpha, n, out, off=0, out_off=0):
+        rc = self.lib.gpar_mean_identity(self.addr(y, off), self.addr(d, off), self.epsilon, self.addr(alpha, off), n,
+                                         self.addr(out, out_off), self.stream)
+        check(rc, "gpar_mean_identity")
+        self.launches += 1 if n > 0 else 0
+
+    def mean_axis0(self, inp, ns, n, out):
+        rc = self.lib.gpar_mean_axis0(self.addr(inp), ns, n, self.addr(out), self.stream)
+        check(rc, "gpar_mean_axis0")
+        self.launches += 1
+
+    def fp64_probe(self, mode, iters):
+        sink = self.zeros(2)
+        flops = C.c_double(0.0)
+        rc = self.lib.gpar_fp64_probe(mode, iters, self.addr(sink), C.byref(flops), self.stream)
+        check(rc, "gpar_fp64_probe")
+        self.launches += 1
+        return flops.value
+
+
+class Factor:
+    """Cholesky of ``K(X, X) + diag(d) + eps I`` over the stacked rows ``X`` =
+    [observation rows (n_obs); appended test rows (n_ext)] with the right-hand
+    side ``y`` riding along as an appended row of the sweep.  One gpar_potrf call
+    yields:
+
+    * ``L``  = lower factor of the whole joint matrix (in ``J``), whose blocks are
+      ``L_oo`` (observations), ``W = K_*o L_oo^-T`` and ``C = chol(K_** + D_* + eps I - W W^T)``;
+    * ``u``  = ``L_oo^-1 y`` (first ``n_obs`` entries of the appended row).
+    """
+
+    def __init__(self, eng, spec, X, ldx, d, y, n_obs, n_ext=0):
+        self.eng, self.spec = eng, spec
+        self.X, self.ldx, self.d, self.y = X, ldx, d, y
+        self.n_obs, self.n_ext = int(n_obs), int(n_ext)
+        n = self.n = self.n_obs + self.n_ext
+        self.ld = ld = _even(max(n, 2))
+        self.J = eng.empty(max(n, 1) * ld)
+        self.u = eng.zeros(ld)
+        if self.n_obs > 0:
+            self.u[: self.n_obs].copy_(y[: self.n_obs])
+        self._alpha = None
+        if n > 0:
+            eng.gram(spec, X, ldx, n, self.J, ld, diag=d, lower_only=True)
+            self.ws, self.info = eng.potrf(self.J, ld, n, B=self.u, ldb=ld, nb=1)
+        else:
+            self.ws, self.info = eng.empty(2), torch.zeros(1, dtype=torch.int32, device=eng.device)
+
+    def logdet_quad(self, out2, out_off, r0, r1):
+        """out2[out_off:out_off+2] = (2 sum_{r0<=i<r1} log L_ii, sum u_i^2)."""
+        self.eng.logdet_quad(self.J, self.ld, r1 - r0, self.u, out2, l_off=r0 * self.ld + r0, u_off=r0, out_off=out_off)
+
+    def alpha(self):
+        """alpha = (K + D + eps I)^-1 y over the observation rows."""
+        if self._alpha is None:
+            self._alpha = self.eng.backsolve(self.J, self.ld, self.n_obs, self.ws, self.u)
+        return self._alpha
+
+    def mean_obs(self, out, r0, r1, out_off=0):
+        """Posterior mean at observation rows [r0, r1): y - (d + eps) alpha, the exact
+        identity K alpha = y - (D + eps I) alpha (no n^2 work)."""
+        self.eng.mean_identity(self.y, self.d, self.alpha(), r1 - r0, out, off=r0, out_off=out_off)
+
+    def mean_at(self, Xq, ldq, nq, out):
+        """Posterior mean at arbitrary rows: K(Xq, X_obs) alpha, fused (no cross-Gram in HBM)."""
+        if self.n_obs == 0:
+            out[:nq].zero_()
+            return
+        self.eng.gram_gemv(self.spec, Xq, ldq, nq, self.X, self.ldx, self.n_obs, self.alpha(), out)
+
+    def ext_mean(self, out):
+        """Posterior mean at the appended rows: W u."""
+        if self.n_obs == 0:
+            out[: self.n_ext].zero_()
+            return
+        self.eng.gemv(self.J, self.ld, self.n_ext, self.n_obs, self.u, out, a_off=self.n_obs * self.ld)
+
+    def ext_sample(self, Z, ns, out, mean=None, sd=None, Z2=None):
+        """out[s] = mean + C Z[s] (+ sd * Z2[s]) with C the factor of the posterior
+        covariance at the appended rows (joint draw)."""
+        self.eng.sample_affine(self.J, self.ld, self.n_ext, Z, out, ns, mean=mean, sd=sd, Z2=Z2,
+                               c_off=self.n_obs * self.ld + self.n_obs)

@@ -1,0 +1,208 @@
+"""GPARRegressor with the API of gpar/regression.py:200-597, running the per-layer
+GP arithmetic on the B200 engine.  Host code here is data preparation only
+(transforms, normalisation, hyper-parameter bookkeeping, the optimiser loop)."""
+import numpy as np
+from scipy.optimize import minimize
+
+from .model import GPAR, per_output
+from .spec import LayerModel, Vars, model_terms
+
+__all__ = ["GPARRegressor", "log_transform", "squishing_transform"]
+
+#: Log transform for the data (regression.py:22).
+log_transform = (np.log, np.exp)
+
+#: Squishing transform for the data (regression.py:25-28).
+squishing_transform = (
+    lambda x: np.sign(x) * np.log(1 + np.abs(x)),
+    lambda x: np.sign(x) * (np.exp(np.abs(x)) - 1),
+)
+
+
+def _identity(x):
+    return x
+
+
+def _uprank(a):
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 0:
+        a = a[None]
+    return a[:, None] if a.ndim == 1 else a
+
+
+def _construct_gpar(reg, vs, m, p):
+    """Layer-by-layer construction (regression.py:185-190); each constructor re-reads
+    the hyper-parameters from ``vs`` when called, like ``_model_generator``'s closure."""
+    gpar = GPAR(replace=reg.replace, impute=reg.impute, x_ind=reg.x_ind, engine=reg._engine)
+    for pi in range(p):
+        def model(pi=pi):
+            terms, noise = model_terms(vs, m, pi, **reg.model_config)
+            return LayerModel(terms, noise)
+        gpar = gpar.add_layer(model)
+    return gpar
+
+
+def _init_weights(w, y):
+    return np.ones_like(y) if w is None else _uprank(w)
+
+
+class GPARRegressor:
+    """GPAR regressor; arguments, attributes and error behaviour follow
+    gpar/regression.py:200-326 (code defaults win over the docstring, quirk Q2).
+
+    Extra args:
+        engine: :class:`gpar_b200.engine.Engine` to run on (default: shared engine
+            on the current CUDA device).
+    """
+
+    def __init__(self, replace=False, impute=True, scale=1.0, scale_tie=False, per=False, per_period=1.0,
+                 per_scale=1.0, per_decay=10.0, input_linear=False, input_linear_scale=100.0, linear=True,
+                 linear_scale=100.0, nonlinear=False, nonlinear_scale=1.0, rq=False, markov=None, noise=0.1,
+                 x_ind=None, normalise_y=True, transform_y=(_identity, _identity), engine=None):
+        self.replace = replace
+        self.impute = impute
+        self.sparse = x_ind is not None
+        self.x_ind = None if x_ind is None else _uprank(x_ind)
+        self.model_config = {
+            "scale": scale, "scale_tie": scale_tie, "per": per, "per_period": per_period, "per_scale": per_scale,
+            "per_decay": per_decay, "input_linear": input_linear, "input_linear_scale": input_linear_scale,
+            "linear": linear, "linear_scale": linear_scale, "nonlinear": nonlinear,
+            "nonlinear_scale": nonlinear_scale, "rq": rq, "markov": markov, "noise": noise,
+        }
+        self.vs = Vars()
+        self.is_conditioned = False
+        self.x = self.y = self.w = None
+        self.n = self.m = self.p = None
+        self.normalise_y = normalise_y
+        self._unnormalise_y, self._normalise_y = _identity, _identity
+        self._transform_y, self._untransform_y = transform_y
+        self._engine = engine
+
+    def get_variables(self):
+        """Dictionary of all hyper-parameters (regression.py:328-337)."""
+        return {name: np.array(self.vs[name]) for name in self.vs.names}
+
+    def condition(self, x, y, w=None):
+        """Store (transformed, normalised) data; no GP arithmetic (regression.py:339-389).
+        The per-output std is the population std (ddof = 0)."""
+        self.x = _uprank(x)
+        self.y = self._transform_y(_uprank(y))
+        self.w = _init_weights(w, self.y)
+        self.n, self.m = self.x.shape
+        self.p = self.y.shape[1]
+        if self.normalise_y:
+            means, stds = [], []
+            for i in range(self.p):
+                y_i = self.y[~np.isnan(self.y[:, i]), i]
+                means.append(np.mean(y_i))
+                std = np.std(y_i)
+                stds.append(std if std > 0 else 1.0)
+            means, stds = np.array(means)[None, :], np.array(stds)[None, :]
+            self._normalise_y = lambda y_: (y_ - means) / stds
+            self._unnormalise_y = lambda y_: y_ * stds + means
+            self.y = self._normalise_y(self.y)
+        self.is_conditioned = True
+
+    def fit(self, x, y, w=None, greedy=False, fix=True, **kw_args):
+        """Layer-wise maximum likelihood (regression.py:391-459).  ``iters`` and other
+        keyword arguments go to the L-BFGS-B driver.  Gradients are finite differences
+        of the device log-marginal (analytic gradient kernels are SURVEY 8(f)-1)."""
+        self.condition(x, y, w)
+        if greedy:
+            raise NotImplementedError("Greedy search is not implemented yet.")
+        y_cached = {k: list(per_output(self.y, self.w, keep=k)) for k in [True, False]}
+        iters = int(kw_args.pop("iters", 1000))
+        for pi in range(self.p):
+            if fix:
+                gpar = _construct_gpar(self, self.vs, self.m, pi + 1)
+                fixed_x, fixed_x_ind = gpar.logpdf(self.x, y_cached, None, only_last_layer=True,
+                                                   outputs=list(range(pi)), return_inputs=True)
+            # Instantiate the variables of the layers being optimised.
+            for ctor in _construct_gpar(self, self.vs, self.m, pi + 1).layers:
+                ctor()
+            names = self.vs.match([f"{pi}/*"] if fix else [f"{i}/*" for i in range(pi + 1)])
+
+            def objective(z):
+                self.vs.set_latent_vector(names, z)
+                gpar = _construct_gpar(self, self.vs, self.m, pi + 1)
+                try:
+                    if fix:
+                        val = -gpar.logpdf(fixed_x, y_cached, None, only_last_layer=True, outputs=[pi],
+                                           x_ind=fixed_x_ind)
+                    else:
+                        val = -gpar.logpdf(self.x, y_cached, None, only_last_layer=False)
+                except Exception:
+                    return 1e300
+                return val if np.isfinite(val) else 1e300
+
+            z0 = self.vs.get_latent_vector(names)
+            res = minimize(objective, z0, method="L-BFGS-B", options={"maxiter": iters, **kw_args})
+            self.vs.set_latent_vector(names, res.x)
+
+    def logpdf(self, x, y, w=None, sample_missing=False, posterior=False, normals=None):
+        """Log-density of observations (regression.py:461-506).  As in the reference the
+        incoming ``y`` goes through ``_unnormalise_y`` (quirk Q1)."""
+        x = _uprank(x)
+        y = self._unnormalise_y(self._transform_y(_uprank(y)))
+        w = _init_weights(w, y)
+        m, p = x.shape[1], y.shape[1]
+        if posterior and not self.is_conditioned:
+            raise RuntimeError("Must condition or fit model before computing the logpdf under the posterior.")
+        gpar = _construct_gpar(self, self.vs, m, p)
+        if posterior:
+            gpar = gpar | (self.x, self.y, self.w)
+        return np.float64(gpar.logpdf(x, y, w, only_last_layer=False, sample_missing=sample_missing,
+                                      normals=normals))
+
+    def _sample_device(self, x, w, p, posterior, num_samples, latent, normals):
+        x = _uprank(x)
+        if posterior and not self.is_conditioned:
+            raise RuntimeError("Must condition or fit model before sampling from the posterior.")
+        elif not posterior and p is None:
+            raise ValueError("Must specify number of outputs to sample.")
+        if w is None:
+            w = np.ones((x.shape[0], self.p if posterior else p))
+        else:
+            w = _uprank(w)
+        if posterior:
+            # The reference re-conditions on every call (regression.py:546-547); here the
+            # conditioning is fused into the sampling sweep (one joint factor per layer).
+            gpar = _construct_gpar(self, self.vs, self.m, self.p)
+            return gpar.sample(x, w, latent=latent, num_samples=num_samples, normals=normals,
+                               train=(self.x, self.y, self.w), return_device=True)
+        gpar = _construct_gpar(self, self.vs, x.shape[1], p)
+        return gpar.sample(x, w, latent=latent, num_samples=num_samples, normals=normals, return_device=True)
+
+    def sample(self, x, w=None, p=None, posterior=False, num_samples=1, latent=False, normals=None):
+        """Sample from the prior or posterior (regression.py:508-564).  ``normals``
+        injects the standard normals (see :meth:`GPAR.sample`)."""
+        dev = self._sample_device(x, w, p, posterior, num_samples, latent, normals)
+        host = dev.cpu().numpy()
+        samples = [self._untransform_y(self._unnormalise_y(host[s])) for s in range(host.shape[0])]
+        return samples[0] if num_samples == 1 else samples
+
+    def predict(self, x, w=None, num_samples=100, latent=False, credible_bounds=False, normals=None):
+        """Predictive means (and 95% credible bounds) from posterior samples
+        (regression.py:566-597).  With the identity transform and no bounds the
+        sample mean is reduced on the device and only (n*, p) values come back."""
+        if self._untransform_y is _identity and not credible_bounds:
+            dev = self._sample_device(x, w, None, True, num_samples, latent, normals)
+            S, ns, p = dev.shape
+            eng = self._engine_of(dev)
+            out = eng.empty(max(ns * p, 1))
+            eng.mean_axis0(dev.reshape(-1), S, ns * p, out)
+            return self._unnormalise_y(out.cpu().numpy().reshape(ns, p))
+        samples = self.sample(x, w, num_samples=num_samples, latent=latent, posterior=True, normals=normals)
+        if num_samples == 1:
+            samples = [samples]
+        mean = np.mean(samples, axis=0)
+        if credible_bounds:
+            lowers = np.percentile(samples, 2.5, axis=0)
+            uppers = np.percentile(samples, 100 - 2.5, axis=0)
+            return mean, lowers, uppers
+        return mean
+
+    def _engine_of(self, _):
+        from .model import default_engine
+
+        return self._engine if self._engine is not None else default_engine()

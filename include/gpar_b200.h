@@ -1,0 +1,154 @@
+/*
+ * gpar_b200 -- C ABI of the B200-native (sm_100a) per-layer GP hot path of GPAR.
+ *
+ * The reference (wesselb/gpar) has no FFI: its hot path is the stheno object
+ * protocol driven from gpar/model.py.  Each entry point
+ * below names the protocol element / call site it replaces.  The caller is the
+ * host p-loop in gpar_b200/model.py (ctypes); every pointer is caller-owned
+ * DEVICE memory (torch CUDA tensors), `stream` is a cudaStream_t passed as
+ * void*.  Nothing is retained after a call returns; work is ordered on
+ * `stream`.  All matrices are row-major fp64 with a leading dimension in
+ * ELEMENTS; symmetric / triangular matrices keep the LOWER triangle
+ * authoritative (entries above the diagonal are never read and, unless stated,
+ * never written).  Base pointers must be 16-byte aligned and leading
+ * dimensions even (the tile loaders use 16-byte cp.async).
+ *
+ * Return value: 0 = ok, <0 = -(index of the offending argument, 1-based) or a
+ * CUDA launch failure (see gpar_last_error()).  Numerical failure (first
+ * non-positive pivot, LAPACK `info` style, 1-based) is written to the caller's
+ * device `info` word and read back only when the caller chooses to sync.
+ */
+#ifndef GPAR_B200_H
+#define GPAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPAR_ABI_VERSION 1
+#define GPAR_TILE 128        /* Cholesky tile edge; workspace is sized in tiles */
+#define GPAR_MAX_TERMS 8
+#define GPAR_MAX_FEATS 96
+
+/* Kernel terms after lowering to a feature map (see gpar_kernel_spec_t). */
+enum { GPAR_TERM_EQ = 0, GPAR_TERM_RQ = 1, GPAR_TERM_LINEAR = 2, GPAR_TERM_CONST = 3 };
+/* Feature ops: phi = a * x[col], a * sin(b * x[col]), a * cos(b * x[col]). */
+enum { GPAR_FEAT_SCALE = 0, GPAR_FEAT_SIN = 1, GPAR_FEAT_COS = 2 };
+
+typedef struct {
+  int32_t type;     /* GPAR_TERM_* */
+  int32_t f_begin;  /* features [f_begin, f_end) belong to this term */
+  int32_t f_end;
+  int32_t _pad;
+  double variance;  /* multiplier; for CONST the constant itself */
+  double alpha;     /* RQ shape */
+} gpar_term_t;
+
+/*
+ * Closed kernel family of gpar/regression.py:92-180 (`_model_generator`) in
+ * feature-map normal form: k(x, y) = sum_t k_t(phi_t(x), phi_t(y)) with
+ *   EQ:     var * exp(-1/2 ||phi(x) - phi(y)||^2)
+ *   RQ:     var * (1 + ||phi(x) - phi(y)||^2 / (2 alpha))^(-alpha)
+ *   LINEAR: var * <phi(x), phi(y)>
+ *   CONST:  var
+ * `.stretch(s)` becomes a = 1/s; `.select(cols)` becomes feat_col;
+ * `EQ().stretch(s).periodic(T) * EQ().stretch(d)` becomes one EQ term over the
+ * 3m features [sin(2 pi x/T)/s_c, cos(2 pi x/T)/s_{m+c}, x/d_c].
+ */
+typedef struct {
+  int32_t n_terms;
+  int32_t n_feats;
+  gpar_term_t terms[GPAR_MAX_TERMS];
+  int32_t feat_col[GPAR_MAX_FEATS];
+  int32_t feat_op[GPAR_MAX_FEATS];
+  double feat_a[GPAR_MAX_FEATS];
+  double feat_b[GPAR_MAX_FEATS];
+} gpar_kernel_spec_t;
+
+int gpar_abi_version(void);
+const char* gpar_last_error(void);
+
+/* K1 -- Gram matrix.  Replaces mlkernels kernel evaluation `k(x, y)` driven from
+ * regression.py:94-179 and the `+ noise / w` of `f(x, noise / w)` (model.py:287-289).
+ * Y == NULL: symmetric K(X, X); then diag_add (length nx, may be NULL) and eps are
+ * added on the diagonal (K_ii += diag_add[i] + eps) and, if lower_only != 0, tiles
+ * strictly above the diagonal are skipped.  out is nx x ny. */
+int gpar_gram(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t nx,
+              const double* Y, int64_t ldy, int64_t ny, const double* diag_add, double eps,
+              int lower_only, double* out, int64_t ldo, void* stream);
+
+/* Batched form: matrix b uses X + b*strideX, Y + b*strideY, diag_add + b*strideD, out + b*strideO
+ * (strides in elements; a stride of 0 shares the operand across the batch). */
+int gpar_gram_batched(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t nx, int64_t strideX,
+                      const double* Y, int64_t ldy, int64_t ny, int64_t strideY, const double* diag_add,
+                      int64_t strideD, double eps, int lower_only, double* out, int64_t ldo, int64_t strideO,
+                      int64_t batch, void* stream);
+
+/* K2 -- blocked Cholesky (matrix.cholesky -> torch.linalg.cholesky in the reference),
+ * batched, with optional appended row blocks.  For each b < batch:
+ *   A_b (n x n, lower) <- L_b with L_b L_b^T = A_b;   B_b (nb x n) <- B_b L_b^-T.
+ * B may be NULL (nb = 0).  `ws` receives the inverses of the diagonal GPAR_TILE
+ * blocks of L (gpar_potrf_workspace_bytes(n, batch) bytes, 16-byte aligned); keep it
+ * for gpar_trsm_rows / gpar_backsolve.  info[b] = 0 or 1-based index of the first
+ * non-positive pivot. */
+size_t gpar_potrf_workspace_bytes(int64_t n, int64_t batch);
+int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, double* B, int64_t ldb, int64_t nb,
+               int64_t strideB, int64_t batch, double* ws, int32_t* info, void* stream);
+
+/* K4 -- B (nb x n) <- B L^-T given L and the `ws` of its gpar_potrf.  This is
+ * (L^-1 K(x_a, x_))^T of PosteriorMean / PosteriorKernel. */
+int gpar_trsm_rows(const double* L, int64_t ldl, int64_t n, const double* ws, double* B, int64_t ldb,
+                   int64_t nb, void* stream);
+
+/* K5 -- C_b (n x n, lower) <- C_b - W_b W_b^T, W_b is n x k.  Posterior covariance
+ * K** - V^T V. */
+int gpar_syrk_sub(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw, int64_t k,
+                  int64_t strideW, int64_t batch, void* stream);
+
+/* K3 -- alpha <- L^-T u (u is read only; `work` is n doubles of scratch);
+ * out2[0] = 2 sum log L_ii, out2[1] = ||u||^2.  Normal.logpdf tail / iqf. */
+int gpar_backsolve(const double* L, int64_t ldl, int64_t n, const double* ws, const double* u, double* alpha,
+                   double* work, void* stream);
+int gpar_logdet_quad(const double* L, int64_t ldl, int64_t n, const double* u, double* out2, void* stream);
+
+/* K6 -- y <- A x (A m x n row major) and the fused cross-covariance product
+ * out[j] = sum_i k(Xq[j], Xa[i]) v[i] (posterior mean K(x_, x_a) alpha without
+ * materialising K; model.py:298-301). */
+int gpar_gemv(const double* A, int64_t lda, int64_t m, int64_t n, const double* x, double* y, void* stream);
+int gpar_gram_gemv(const gpar_kernel_spec_t* spec, const double* Xq, int64_t ldq, int64_t nq, const double* Xa,
+                   int64_t lda, int64_t na, const double* v, double* out, void* stream);
+
+/* K7 -- joint Gaussian draws with injected normals (Normal.sample; model.py:264-270):
+ * for b < batch, s < ns:  out[b][s][i] = mean_b[i] + sum_{j<=i} C_b[i][j] Z[b][s][j]
+ *                                        (+ sd_b[i] * Z2[b][s][i] when Z2 != NULL).
+ * Z/out are (batch*ns) x n row major; mean (stride n) and sd may be NULL. */
+int gpar_sample_affine(const double* C, int64_t ldc, int64_t n, int64_t strideC, const double* mean,
+                       const double* sd, const double* Z, const double* Z2, int64_t ns, int64_t batch,
+                       double* out, void* stream);
+
+/* K9 -- row gather / column scatter used by per_output masks and `_update_inputs`
+ * (model.py:165,220,291-322).  idx are int64 row indices (device). */
+int gpar_gather_rows(const double* src, int64_t lds, const int64_t* idx, int64_t n_out, int64_t ncols, double* dst,
+                     int64_t ldd, void* stream);
+int gpar_scatter_col(double* dst, int64_t ldd, int64_t col, const int64_t* idx, const double* src, int64_t n,
+                     void* stream);
+/* out[i] = y[i] - (d[i] + eps) * alpha[i]: posterior mean at the training rows via the
+ * identity K alpha = y - (Sigma + eps I) alpha. */
+int gpar_mean_identity(const double* y, const double* d, double eps, const double* alpha, int64_t n, double* out,
+                       void* stream);
+
+/* Device-side reductions over the sample axis (regression.py:589): out[i] = mean_s in[s][i]. */
+int gpar_mean_axis0(const double* in, int64_t ns, int64_t n, double* out, void* stream);
+
+/* Diagnostics: raw fp64 issue-rate probes used by bench.py to state the roofline
+ * denominators next to cuBLAS DGEMM.  mode 0 = DMMA m8n8k4, 1 = DFMA.  Returns the
+ * number of flops executed per launch through *flops. */
+int gpar_fp64_probe(int mode, int64_t iters, double* sink, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPAR_B200_H */

@@ -161,7 +161,8 @@ def vector_from_init(init, length):
 def _sqdist(X, Y, cols, inv_scale):
     d2 = np.zeros((X.shape[0], Y.shape[0]))
     for c, s in zip(cols, inv_scale):
-        diff = (X[:, c][:, None] - Y[:, c][None, :]) * s
+        # ``.stretch``: inputs are scaled first, then differenced (mlkernels order).
+        diff = (X[:, c] * s)[:, None] - (Y[:, c] * s)[None, :]
         d2 += diff * diff
     return d2
 
@@ -197,8 +198,8 @@ def kernel_matrix(terms, X, Y):
             d2 = np.zeros_like(K)
             for j, c in enumerate(cols):
                 ax, ay = X[:, c] * freq[j], Y[:, c] * freq[j]
-                ds = (np.sin(ax)[:, None] - np.sin(ay)[None, :]) * inv_scale[j]
-                dc = (np.cos(ax)[:, None] - np.cos(ay)[None, :]) * inv_scale[m + j]
+                ds = (inv_scale[j] * np.sin(ax))[:, None] - (inv_scale[j] * np.sin(ay))[None, :]
+                dc = (inv_scale[m + j] * np.cos(ax))[:, None] - (inv_scale[m + j] * np.cos(ay))[None, :]
                 d2 += ds * ds
                 d2 += dc * dc
             K += var * np.exp(-0.5 * d2) * np.exp(-0.5 * _sqdist(X, Y, cols, inv_decay))

@@ -1,0 +1,150 @@
+"""CPU tests of the product's host logic (bit-exact integer path against the reference's
+golden vectors) and of the C-ABI shared library: it must load and export every symbol that
+include/gpar_b200.h declares.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gpar_b200 import _lib
+from gpar_b200.model import last, merge, per_output
+from gpar_b200.spec import LayerModel, Vars, determine_indices, lower_terms, model_terms, vector_from_init
+from tests.test_oracle_golden import DETERMINE_GOLDEN, EXPECTED_KEEP_FALSE, EXPECTED_KEEP_TRUE, Y_GOLDEN
+from oracle import gpar_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_merge_last_golden():
+    original = np.array([1, 2, 3, 4])
+    updates = np.array([5, 6])
+    assert merge(original, updates, np.array([True, True, False, False])).tolist() == [5, 6, 3, 4]
+    assert merge(original, updates, np.array([True, False, True, False])).tolist() == [5, 2, 6, 4]
+    xs = [1, 2, 3, 4]
+    assert list(last(xs)) == [(False, 1), (False, 2), (False, 3), (True, 4)]
+    assert list(last(xs, [1, 2])) == [(False, 2), (False, 3)]
+    assert list(last(xs, [0, 3])) == [(False, 1), (True, 4)]
+    assert list(last([])) == []
+    assert list(last([], [0, 1])) == []
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_per_output_golden(which):
+    def run(keep):
+        out = []
+        for yi, wi, mask in per_output(Y_GOLDEN, Y_GOLDEN, keep=keep):
+            v = yi[:, 0] if which == 0 else wi
+            out.append(([None if np.isnan(c) else c for c in v.tolist()], mask.tolist()))
+        return out
+
+    assert run(False) == EXPECTED_KEEP_FALSE
+    assert run(True) == EXPECTED_KEEP_TRUE
+    assert list(per_output({True: [2, 3], False: [4]}, None, keep=False)) == [4]
+
+
+def test_per_output_matches_oracle_random():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        n, p = rng.integers(1, 40), rng.integers(1, 6)
+        y = rng.standard_normal((n, p))
+        y[rng.uniform(size=(n, p)) < 0.35] = np.nan
+        w = rng.uniform(size=(n, p))
+        for keep in (False, True):
+            a = list(per_output(y, w, keep=keep))
+            b = list(O.per_output(y, w, keep=keep))
+            assert len(a) == len(b)
+            for (ya, wa, ma), (yb, wb, mb) in zip(a, b):
+                assert np.array_equal(ma, mb)
+                assert np.array_equal(ya, yb, equal_nan=True) and np.array_equal(wa, wb)
+
+
+@pytest.mark.parametrize("args,expected", DETERMINE_GOLDEN)
+def test_determine_indices_golden(args, expected):
+    assert determine_indices(*args) == expected
+
+
+def test_vector_from_init():
+    assert vector_from_init(2, 2).tolist() == [2, 2]
+    assert vector_from_init(np.array([1, 2, 3]), 2).tolist() == [1, 2]
+    with pytest.raises(ValueError):
+        vector_from_init(np.random.randn(2, 2), 1)
+    with pytest.raises(ValueError):
+        vector_from_init(np.array([1, 2]), 3)
+
+
+def test_model_terms_match_oracle_and_names():
+    cfg = dict(scale=0.5, scale_tie=False, per=True, per_period=2.0, per_scale=1.5, per_decay=10.0, input_linear=True,
+               input_linear_scale=3.0, linear=True, linear_scale=7.0, nonlinear=True, nonlinear_scale=0.3, rq=True,
+               markov=2, noise=[0.1, 0.2, 0.3, 0.4])
+    vs, vo = Vars(), O._Vars()
+    for pi in range(4):
+        ta, na = model_terms(vs, 2, pi, **cfg)
+        tb, nb = O.model_terms(vo, 2, pi, **cfg)
+        assert na == nb and len(ta) == len(tb)
+        for a, b in zip(ta, tb):
+            assert a["type"] == b["type"] and list(a.get("cols", [])) == list(b.get("cols", []))
+    assert sorted(vs.names) == sorted(vo.values.keys())
+    assert "3/output/nonlin/alpha" in vs and "2/input/per/pers" in vs and "1/input/lin/const" in vs
+    vt = Vars()
+    model_terms(vt, 2, 0, **{**cfg, "scale_tie": True})
+    model_terms(vt, 2, 1, **{**cfg, "scale_tie": True})
+    assert "0/input/scales" in vt and "1/input/scales" not in vt
+
+
+def test_lower_terms_feature_form():
+    terms = [dict(type="eq", variance=2.0, cols=[0, 1], scales=[0.5, 4.0]),
+             dict(type="periodic", variance=1.5, cols=[0, 1], scales=[1, 2, 3, 4], periods=[2.0, 4.0], decays=[10, 20]),
+             dict(type="linear", variance=1.0, cols=[], scales=[]),
+             dict(type="const", variance=0.7),
+             dict(type="rq", variance=1.0, cols=[3], scales=[2.0], alpha=0.01)]
+    s = lower_terms(terms)
+    assert s.n_terms == 4 and s.n_feats == 2 + 6 + 0 + 1
+    assert [s.terms[i].type for i in range(4)] == [_lib.TERM_EQ, _lib.TERM_EQ, _lib.TERM_CONST, _lib.TERM_RQ]
+    assert (s.terms[1].f_begin, s.terms[1].f_end) == (2, 8)
+    assert [s.feat_op[i] for i in range(2, 8)] == [1, 1, 2, 2, 0, 0]
+    assert s.feat_a[0] == 2.0 and s.feat_a[1] == 0.25 and s.feat_a[4] == 1 / 3 and s.feat_a[7] == 1 / 20
+    assert abs(s.feat_b[2] - np.pi) < 1e-15 and s.feat_col[8] == 3
+    f, noise = LayerModel(terms, 0.3)
+    assert noise == 0.3 and f.spec.n_terms == 4
+
+
+def test_vars_latent_roundtrip():
+    vs = Vars()
+    vs.bnd("a", np.array([0.5, 2.0]))
+    vs.bnd("b", 1e-2, lower=1e-3, upper=1e3)
+    vs.get("c", 1.0)
+    names = ["a", "b", "c"]
+    z = vs.get_latent_vector(names)
+    vs2 = vs.copy()
+    vs2.set_latent_vector(names, z)
+    for nme in names:
+        np.testing.assert_allclose(vs2[nme], vs[nme], rtol=1e-12)
+
+
+def test_shared_library_exports_header_symbols():
+    header = open(os.path.join(ROOT, "include", "gpar_b200.h")).read()
+    declared = set(re.findall(r"\b(gpar_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gpar_kernel_spec_t", "gpar_term_t"}
+    assert len(declared) >= 18
+    assert os.path.exists(_lib.LIB_PATH), "run `python -m gpar_b200.build` (build() does this)"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert _lib.load().gpar_abi_version() == 1
+    # struct layout must match the header (terms are 32 B, spec = 8 + 8*32 + 96*(4+4+8+8))
+    assert ctypes.sizeof(_lib.Term) == 32
+    assert ctypes.sizeof(_lib.KernelSpec) == 8 + 8 * 32 + 96 * 24
+
+
+def test_engine_fails_loudly_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from gpar_b200.engine import Engine
+
+    with pytest.raises(_lib.GparError):
+        Engine()
