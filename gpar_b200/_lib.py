@@ -57,9 +57,10 @@ SIGNATURES = {
     "gpar_gram": (_int, [_SPEC, _p, _i64, _i64, _p, _i64, _i64, _p, _d, _int, _p, _i64, _p]),
     "gpar_gram_batched": (_int, [_SPEC, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _d, _int, _p, _i64,
                                  _i64, _i64, _p]),
-    "gpar_potrf_workspace_bytes": (C.c_size_t, [_i64, _i64]),
+    "gpar_potrf_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64]),
+    "gpar_trsm_rows_scratch_bytes": (C.c_size_t, [_i64]),
     "gpar_potrf": (_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
-    "gpar_trsm_rows": (_int, [_p, _i64, _i64, _p, _p, _i64, _i64, _p]),
+    "gpar_trsm_rows": (_int, [_p, _i64, _i64, _p, _p, _i64, _i64, _p, _p]),
     "gpar_syrk_sub": (_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p]),
     "gpar_backsolve": (_int, [_p, _i64, _i64, _p, _p, _p, _p, _p]),
     "gpar_logdet_quad": (_int, [_p, _i64, _i64, _p, _p, _p]),

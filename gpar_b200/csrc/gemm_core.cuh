@@ -127,4 +127,22 @@ __device__ __forceinline__ void store_tile(double* __restrict__ C, int64_t ldc, 
   }
 }
 
+// C = C2 + acc (C2 is a dense tile with leading dimension ldc2).
+__device__ __forceinline__ void store_tile_add(double* __restrict__ C, int64_t ldc, const double* __restrict__ C2,
+                                               int64_t ldc2, int rows, int cols, const Acc& acc) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = wm * 32 + i * 8 + gid;
+    if (r >= rows) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = wn * 64 + j * 8 + 2 * tig;
+      if (c < cols) C[(int64_t)r * ldc + c] = C2[(int64_t)r * ldc2 + c] + acc[i][j][0];
+      if (c + 1 < cols) C[(int64_t)r * ldc + c + 1] = C2[(int64_t)r * ldc2 + c + 1] + acc[i][j][1];
+    }
+  }
+}
+
 }  // namespace gpar

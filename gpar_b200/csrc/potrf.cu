@@ -20,6 +20,7 @@ constexpr int DLD = 129;  // row stride of the tile in shared memory
 constexpr int ILD = 33;   // row stride of a 32x32 inverse block
 constexpr int NB32 = TILE / 32;
 constexpr int NINV = NB32 * (NB32 + 1) / 2;  // 10 lower blocks
+constexpr double REFINE_KAPPA = 1.0e3;  // kappa_inf(L_kk) above which the tile solves are refined
 constexpr size_t DIAG_SMEM_BYTES = sizeof(double) * (TILE * DLD + NINV * 32 * ILD + TILE) + 16;
 
 __device__ __forceinline__ int blk(int b, int a) { return b * (b + 1) / 2 + a; }
@@ -95,8 +96,8 @@ __device__ __forceinline__ void strip_mma(double (&c)[NTN][2], int K, FA a, FB b
 }
 
 __global__ void __launch_bounds__(256, 1)
-potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, int64_t n, double* __restrict__ ws,
-                  int64_t strideWs, int32_t* __restrict__ info) {
+potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, int nt_total, int64_t n,
+                  double* __restrict__ ws, int64_t strideWs, int32_t* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Ls = reinterpret_cast<double*>(smem_raw);
   double* Inv = Ls + TILE * DLD;
@@ -105,6 +106,7 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, 
 
   const int b = blockIdx.x;
   A += (int64_t)b * strideA;
+  double* flags = ws + (int64_t)b * strideWs + (int64_t)nt_total * TILE * TILE;
   ws += (int64_t)b * strideWs + (int64_t)kt * TILE * TILE;
   const int64_t j0 = (int64_t)kt * TILE;
   const int kb = static_cast<int>(min64(TILE, n - j0));
@@ -130,20 +132,47 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, 
     __syncthreads();
     const int rem = TILE - (o + 32);
     if (rem == 0) break;
-    // panel: X = T inv_aa^T, T = rows [o+32, 128) x cols [o, o+32)   (in place, warp owns whole rows)
+    // panel: X = T L_aa^-T, T = rows [o+32, 128) x cols [o, o+32) (in place, a warp owns whole rows).
+    // X0 = T inv^T, then one step of iterative refinement against L_aa itself
+    // (R = T - X0 L_aa^T, X = X0 + R inv^T) so that the solve stays backward stable when the
+    // block is ill-conditioned (explicit inverses alone lose a factor cond(L_aa)).
     {
       const double* inv = Inv + blk(a, a) * 32 * ILD;
+      const double* Laa = Ls + o * DLD + o;
       for (int strip = warp; strip < rem / 8; strip += 8) {
         double* T = Ls + (o + 32 + strip * 8) * DLD + o;
-        double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-        strip_mma<4>(
-            c, 32, [&](int m, int k) { return T[m * DLD + k]; }, [&](int k, int nn) { return inv[nn * ILD + k]; }, gid,
-            tig);
+        auto fa = [&](int m, int k) { return T[m * DLD + k]; };
+        auto finv = [&](int k, int nn) { return inv[nn * ILD + k]; };
+        auto flt = [&](int k, int nn) { return (k <= nn) ? Laa[nn * DLD + k] : 0.0; };
+        double t0[4][2], x0[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          t0[t][0] = T[gid * DLD + t * 8 + 2 * tig];
+          t0[t][1] = T[gid * DLD + t * 8 + 2 * tig + 1];
+        }
+        strip_mma<4>(x0, 32, fa, finv, gid, tig);
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          T[gid * DLD + t * 8 + 2 * tig] = c[t][0];
-          T[gid * DLD + t * 8 + 2 * tig + 1] = c[t][1];
+          T[gid * DLD + t * 8 + 2 * tig] = x0[t][0];
+          T[gid * DLD + t * 8 + 2 * tig + 1] = x0[t][1];
+        }
+        __syncwarp();
+        double xl[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        strip_mma<4>(xl, 32, fa, flt, gid, tig);
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          T[gid * DLD + t * 8 + 2 * tig] = t0[t][0] - xl[t][0];
+          T[gid * DLD + t * 8 + 2 * tig + 1] = t0[t][1] - xl[t][1];
+        }
+        __syncwarp();
+        strip_mma<4>(x0, 32, fa, finv, gid, tig);  // x0 += R inv^T
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          T[gid * DLD + t * 8 + 2 * tig] = x0[t][0];
+          T[gid * DLD + t * 8 + 2 * tig + 1] = x0[t][1];
         }
       }
     }
@@ -222,10 +251,45 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, 
     __syncthreads();
   }
 
-  // ---- write back L (lower part of the valid block) and Linv (dense 128x128, zero padded) -----
+  // ---- write back L (valid block; its strictly upper part is zeroed so the tile can serve as a
+  // GEMM operand) and Linv (dense 128x128, zero padded); kappa_inf(L_kk) decides refinement -----
+  double rowL = 0.0, rowI = 0.0;  // thread t < 128 accumulates the abs row sums of row t
+  if (tid < kb) {
+    for (int c = 0; c <= tid; ++c) {
+      rowL += fabs(Ls[tid * DLD + c]);
+      rowI += fabs(Inv[blk(tid >> 5, c >> 5) * 32 * ILD + (tid & 31) * ILD + (c & 31)]);
+    }
+  }
+  // max over the block via shared memory (reuse rdiag as scratch after a barrier)
+  __syncthreads();
+  double* red = rdiag;
+  if (tid < TILE) red[tid] = 0.0;
+  __syncthreads();
+  {
+    double mL = rowL, mI = rowI;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      mL = fmax(mL, __shfl_xor_sync(0xffffffffu, mL, off));
+      mI = fmax(mI, __shfl_xor_sync(0xffffffffu, mI, off));
+    }
+    if (lane == 0) {
+      red[warp] = mL;
+      red[8 + warp] = mI;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mL = 0.0, mI = 0.0;
+    for (int i = 0; i < 8; ++i) {
+      mL = fmax(mL, red[i]);
+      mI = fmax(mI, red[8 + i]);
+    }
+    const double kappa = mL * mI;
+    flags[kt] = (kappa > REFINE_KAPPA || !(kappa == kappa)) ? 1.0 : 0.0;
+  }
   for (int idx = tid; idx < TILE * TILE; idx += 256) {
     const int r = idx >> 7, c = idx & 127;
-    if (r < kb && c <= r) A[(j0 + r) * lda + j0 + c] = Ls[r * DLD + c];
+    if (r < kb && c < kb) A[(j0 + r) * lda + j0 + c] = (c <= r) ? Ls[r * DLD + c] : 0.0;
     double v = 0.0;
     if (r < kb && c <= r) v = Inv[blk(r >> 5, c >> 5) * 32 * ILD + (r & 31) * ILD + (c & 31)];
     ws[idx] = v;
@@ -236,10 +300,38 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, 
 // --------------------------------------------------------------------------------------
 // T (rows x kb) <- T Linv^T for every 128-row tile of a row block.
 // --------------------------------------------------------------------------------------
+// X = T L_kk^-T for one 128-row tile: X0 = T Linv^T; when the diagonal block is flagged
+// ill-conditioned, one refinement step R = T - X0 L_kk^T, X = X0 + R Linv^T (X0 parked in a
+// per-CTA scratch tile) restores backward stability.
+__device__ __forceinline__ void tile_solve(GemmStage* stages, double* __restrict__ T, int64_t ldt, int valid, int kb,
+                                           const double* __restrict__ Linv, const double* __restrict__ Lkk,
+                                           int64_t ldl, bool refine, double* __restrict__ scratch) {
+  Acc acc;
+  acc_zero(acc);
+  gemm_nt_mainloop(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);
+  if (!refine) {
+    store_tile<0>(T, ldt, valid, kb, acc, false);
+    return;
+  }
+  store_tile<0>(scratch, TILE, valid, kb, acc, false);  // X0
+  __threadfence();
+  __syncthreads();
+  acc_zero(acc);
+  gemm_nt_mainloop(stages, scratch, TILE, valid, Lkk, ldl, kb, kb, acc);  // X0 L_kk^T
+  store_tile<1>(T, ldt, valid, kb, acc, false);                            // T <- R = T - X0 L_kk^T
+  __threadfence();
+  __syncthreads();
+  acc_zero(acc);
+  gemm_nt_mainloop(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);  // R Linv^T
+  store_tile_add(T, ldt, scratch, TILE, valid, kb, acc);              // T <- X0 + R Linv^T
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 trsm_tile_kernel(double* __restrict__ T1, int64_t ldt1, int64_t rows1, int64_t strideT1, int nt1,
                  double* __restrict__ T2, int64_t ldt2, int64_t rows2, int64_t strideT2, int kb,
-                 const double* __restrict__ Linv, int64_t strideW) {
+                 const double* __restrict__ Linv, int64_t strideW, const double* __restrict__ Lkk, int64_t ldl,
+                 int64_t strideL, const double* __restrict__ flag, double* __restrict__ scratch,
+                 int64_t strideScratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
   int ti = blockIdx.x;
@@ -253,12 +345,10 @@ trsm_tile_kernel(double* __restrict__ T1, int64_t ldt1, int64_t rows1, int64_t s
     T = T2 + (int64_t)b * strideT2; ldt = ldt2; rows = rows2;
   }
   T += (int64_t)ti * TILE * ldt;
-  Linv += (int64_t)b * strideW;
   const int valid = static_cast<int>(min64(TILE, rows - (int64_t)ti * TILE));
-  Acc acc;
-  acc_zero(acc);
-  gemm_nt_mainloop(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);
-  store_tile<0>(T, ldt, valid, kb, acc, false);
+  const bool refine = flag[(int64_t)b * strideW] != 0.0;
+  tile_solve(stages, T, ldt, valid, kb, Linv + (int64_t)b * strideW, Lkk + (int64_t)b * strideL, ldl, refine,
+             scratch + (int64_t)b * strideScratch + (int64_t)blockIdx.x * TILE * TILE);
 }
 
 // --------------------------------------------------------------------------------------
@@ -315,26 +405,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_sub_kernel(const SubArgs
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 trsm_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const double* __restrict__ ws,
-                 double* __restrict__ B, int64_t ldb, int64_t nb) {
+                 double* __restrict__ B, int64_t ldb, int64_t nb, double* __restrict__ scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
   const int ti = blockIdx.x;
   double* Brow = B + (int64_t)ti * TILE * ldb;
   const int valid = static_cast<int>(min64(TILE, nb - (int64_t)ti * TILE));
   const int nt = static_cast<int>((n + TILE - 1) / TILE);
+  const double* flags = ws + (int64_t)nt * TILE * TILE;
   for (int j = 0; j < nt; ++j) {
     const int kb = static_cast<int>(min64(TILE, n - (int64_t)j * TILE));
-    Acc acc;
     if (j > 0) {
+      Acc acc;
       acc_zero(acc);
       gemm_nt_mainloop(stages, Brow, ldb, valid, L + (int64_t)j * TILE * ldl, ldl, kb, j * TILE, acc);
       store_tile<1>(Brow + (int64_t)j * TILE, ldb, valid, kb, acc, false);
       __threadfence();
       __syncthreads();
     }
-    acc_zero(acc);
-    gemm_nt_mainloop(stages, Brow + (int64_t)j * TILE, ldb, valid, ws + (int64_t)j * TILE * TILE, TILE, kb, kb, acc);
-    store_tile<0>(Brow + (int64_t)j * TILE, ldb, valid, kb, acc, false);
+    tile_solve(stages, Brow + (int64_t)j * TILE, ldb, valid, kb, ws + (int64_t)j * TILE * TILE,
+               L + (int64_t)j * TILE * ldl + (int64_t)j * TILE, ldl, flags[j] != 0.0,
+               scratch + (int64_t)ti * TILE * TILE);
     __threadfence();
     __syncthreads();
   }
@@ -354,10 +445,21 @@ static void set_smem_attrs() {
 
 using namespace gpar;
 
-extern "C" size_t gpar_potrf_workspace_bytes(int64_t n, int64_t batch) {
+// Workspace layout per matrix (doubles): [nt inverse tiles][nt flags, padded to even]
+// [(nt + nbt) scratch tiles for the refined solves].
+static int64_t ws_flags_off(int64_t nt) { return nt * TILE * TILE; }
+static int64_t ws_scratch_off(int64_t nt) { return nt * TILE * TILE + ((nt + 1) & ~(int64_t)1); }
+static int64_t ws_stride(int64_t nt, int64_t nbt) { return ws_scratch_off(nt) + (nt + nbt) * TILE * TILE; }
+
+extern "C" size_t gpar_potrf_workspace_bytes(int64_t n, int64_t nb, int64_t batch) {
   if (n <= 0 || batch <= 0) return 0;
-  int64_t nt = (n + TILE - 1) / TILE;
-  return (size_t)batch * (size_t)nt * TILE * TILE * sizeof(double);
+  const int64_t nt = (n + TILE - 1) / TILE, nbt = nb > 0 ? (nb + TILE - 1) / TILE : 0;
+  return (size_t)batch * (size_t)ws_stride(nt, nbt) * sizeof(double);
+}
+
+extern "C" size_t gpar_trsm_rows_scratch_bytes(int64_t nb) {
+  if (nb <= 0) return 0;
+  return (size_t)((nb + TILE - 1) / TILE) * TILE * TILE * sizeof(double);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -381,12 +483,14 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
   cudaMemsetAsync(info, 0, sizeof(int32_t) * batch, stream);
   if (n == 0) return 0;
   const int nt = (int)((n + TILE - 1) / TILE);
-  const int64_t strideWs = (int64_t)nt * TILE * TILE;
-  const int nbt = (int)((nb + TILE - 1) / TILE);
+  const int nbt = nb > 0 ? (int)((nb + TILE - 1) / TILE) : 0;
+  const int64_t strideWs = ws_stride(nt, nbt);
+  double* scratch = ws + ws_scratch_off(nt);
   for (int k = 0; k < nt; ++k) {
     const int64_t j0 = (int64_t)k * TILE;
     const int kb = (int)((n - j0 < TILE) ? (n - j0) : TILE);
-    potrf_diag_kernel<<<(unsigned)batch, 256, DIAG_SMEM_BYTES, stream>>>(A, lda, strideA, k, n, ws, strideWs, info);
+    potrf_diag_kernel<<<(unsigned)batch, 256, DIAG_SMEM_BYTES, stream>>>(A, lda, strideA, k, nt, n, ws, strideWs,
+                                                                       info);
     const int64_t below = n - (j0 + TILE);
     const double* Linv = ws + (int64_t)k * TILE * TILE;
     const int ntr = below > 0 ? (int)((below + TILE - 1) / TILE) : 0;
@@ -394,7 +498,8 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
       dim3 g((unsigned)(ntr + nbt), (unsigned)batch);
       trsm_tile_kernel<<<g, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(
           below > 0 ? A + (j0 + TILE) * lda + j0 : A, lda, below > 0 ? below : 0, strideA, ntr,
-          nb > 0 ? B + j0 : B, ldb, nb, strideB, kb, Linv, strideWs);
+          nb > 0 ? B + j0 : B, ldb, nb, strideB, kb, Linv, strideWs, A + j0 * lda + j0, lda, strideA,
+          ws + ws_flags_off(nt) + k, scratch, strideWs);
     }
     if (below > 0) {
       SubArgs p;
@@ -412,15 +517,16 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
 }
 
 extern "C" int gpar_trsm_rows(const double* L, int64_t ldl, int64_t n, const double* ws, double* B, int64_t ldb,
-                              int64_t nb, void* stream_) {
+                              int64_t nb, double* scratch, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!L || !aligned16(L) || (ldl & 1) || ldl < n) { set_error("gpar_trsm_rows: bad L"); return -1; }
   if (!ws || !aligned16(ws)) return -4;
   if (nb <= 0 || n <= 0) return 0;
   if (!B || !aligned16(B) || (ldb & 1) || ldb < n) { set_error("gpar_trsm_rows: bad B"); return -5; }
+  if (!scratch || !aligned16(scratch)) { set_error("gpar_trsm_rows: bad scratch"); return -8; }
   set_smem_attrs();
   unsigned g = (unsigned)((nb + TILE - 1) / TILE);
-  trsm_rows_kernel<<<g, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(L, ldl, n, ws, B, ldb, nb);
+  trsm_rows_kernel<<<g, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(L, ldl, n, ws, B, ldb, nb, scratch);
   return check_launch("gpar_trsm_rows");
 }
 

@@ -33,6 +33,19 @@ class Engine:
         self.epsilon = float(epsilon)
         self.launches = 0  # kernels of ours launched so far
         self.flops = 0.0  # algorithmic flops of the dense contractions issued (bookkeeping for bench.py)
+        self._infos = []  # device `info` words of the factorizations issued since the last check
+
+    def check_infos(self):
+        """Read back the pivot status of every factorization issued since the last call (one
+        device->host copy) and raise if any matrix was not positive definite -- the counterpart
+        of the LinAlgError a failed torch Cholesky raises in the reference."""
+        infos, self._infos = self._infos, []
+        if not infos:
+            return
+        vals = torch.cat([i.reshape(-1) for i in infos]).cpu().numpy()
+        if (vals != 0).any():
+            k = int(vals[vals != 0][0])
+            raise _lib.GparError(f"Cholesky failed: matrix not positive definite (first non-positive pivot {k})")
 
     # -- plumbing -----------------------------------------------------------
     @property
@@ -73,7 +86,7 @@ class Engine:
 
     # -- K2 -------------------------------------------------------------------
     def potrf(self, A, lda, n, B=None, ldb=0, nb=0, batch=1, strideA=0, strideB=0, a_off=0):
-        nbytes = self.lib.gpar_potrf_workspace_bytes(n, batch)
+        nbytes = self.lib.gpar_potrf_workspace_bytes(n, nb, batch)
         ws = self.empty(max(nbytes // 8, 2))
         info = torch.zeros(batch, dtype=torch.int32, device=self.device)
         rc = self.lib.gpar_potrf(self.addr(A, a_off), lda, n, strideA, None if B is None else self.addr(B), ldb, nb,
@@ -82,10 +95,13 @@ class Engine:
         nt = (n + TILE - 1) // TILE
         self.launches += nt + max(nt - 1, 0) + (nt if nb > 0 else max(nt - 1, 0))
         self.flops += batch * (n ** 3 / 3.0 + nb * float(n) ** 2)
+        self._infos.append(info)
         return ws, info
 
     def trsm_rows(self, L, ldl, n, ws, B, ldb, nb):
-        rc = self.lib.gpar_trsm_rows(self.addr(L), ldl, n, self.addr(ws), self.addr(B), ldb, nb, self.stream)
+        scratch = self.empty(max(self.lib.gpar_trsm_rows_scratch_bytes(nb) // 8, 2))
+        rc = self.lib.gpar_trsm_rows(self.addr(L), ldl, n, self.addr(ws), self.addr(B), ldb, nb, self.addr(scratch),
+                                     self.stream)
         check(rc, "gpar_trsm_rows")
         self.launches += 1
         self.flops += nb * float(n) ** 2

@@ -327,6 +327,7 @@ class GPAR:
                     xd = self._update_inputs_dev(xd, y_i, avail, fac)
                 else:
                     xd = xd.with_col(self.engine.to_device(y_i[:, 0]))
+        self.engine.check_infos()
         return gpar
 
     # -- logpdf -----------------------------------------------------------------
@@ -386,6 +387,7 @@ class GPAR:
                     xd = self._update_inputs_dev(xd, y_i, avail, fac, sampled=sampled)
                 else:
                     xd = xd.with_col(eng.to_device(y_i[:, 0]))
+        eng.check_infos()
         if return_inputs:
             return xd, x_ind
         vals = out2.cpu().numpy()
@@ -511,6 +513,7 @@ class GPAR:
                         xd = self._update_inputs_dev(xd, y_i, avail, fac_obs)
                     else:
                         xd = xd.with_col(eng.to_device(y_i[:, 0]))
+        eng.check_infos()
         if return_device:
             return out.reshape(S, ns, p)
         return out.reshape(S, ns, p).cpu().numpy()

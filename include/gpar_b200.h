@@ -91,17 +91,21 @@ int gpar_gram_batched(const gpar_kernel_spec_t* spec, const double* X, int64_t l
  * batched, with optional appended row blocks.  For each b < batch:
  *   A_b (n x n, lower) <- L_b with L_b L_b^T = A_b;   B_b (nb x n) <- B_b L_b^-T.
  * B may be NULL (nb = 0).  `ws` receives the inverses of the diagonal GPAR_TILE
- * blocks of L (gpar_potrf_workspace_bytes(n, batch) bytes, 16-byte aligned); keep it
- * for gpar_trsm_rows / gpar_backsolve.  info[b] = 0 or 1-based index of the first
- * non-positive pivot. */
-size_t gpar_potrf_workspace_bytes(int64_t n, int64_t batch);
+ * blocks of L, a per-block conditioning flag and scratch tiles
+ * (gpar_potrf_workspace_bytes(n, nb, batch) bytes, 16-byte aligned); keep it for
+ * gpar_trsm_rows / gpar_backsolve.  Solves against a diagonal block with
+ * kappa_inf(L_kk) > 1e3 get one step of iterative refinement (backward stable for
+ * near-singular covariances).  The strictly upper part of each diagonal 128-tile of A
+ * is zeroed.  info[b] = 0 or 1-based index of the first non-positive pivot. */
+size_t gpar_potrf_workspace_bytes(int64_t n, int64_t nb, int64_t batch);
 int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, double* B, int64_t ldb, int64_t nb,
                int64_t strideB, int64_t batch, double* ws, int32_t* info, void* stream);
 
 /* K4 -- B (nb x n) <- B L^-T given L and the `ws` of its gpar_potrf.  This is
  * (L^-1 K(x_a, x_))^T of PosteriorMean / PosteriorKernel. */
+size_t gpar_trsm_rows_scratch_bytes(int64_t nb);
 int gpar_trsm_rows(const double* L, int64_t ldl, int64_t n, const double* ws, double* B, int64_t ldb,
-                   int64_t nb, void* stream);
+                   int64_t nb, double* scratch, void* stream);
 
 /* K5 -- C_b (n x n, lower) <- C_b - W_b W_b^T, W_b is n x k.  Posterior covariance
  * K** - V^T V. */
