@@ -9,6 +9,8 @@
 // Appended rows B (nb x n) ride along as extra row tiles, so B <- B L^-T falls out of the same
 // sweep: with B = y^T this is the forward solve of the log-marginal; with the joint matrix
 // [[K_aa, .], [K_*a, K_**]] the sweep yields L, V^T = K_*a L^-T and chol(K_** - V^T V) at once.
+#include <cstdlib>
+
 #include "gemm_core.cuh"
 
 namespace gpar {
@@ -95,27 +97,22 @@ __device__ __forceinline__ void strip_mma(double (&c)[NTN][2], int K, FA a, FB b
   }
 }
 
-__global__ void __launch_bounds__(256, 1)
-potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, int nt_total, int64_t n,
-                  double* __restrict__ ws, int64_t strideWs, int32_t* __restrict__ info) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// Factor one diagonal tile in shared memory (all 256 threads of the CTA): Atile points at
+// A[j0][j0]; on return the tile holds L_kk (strictly upper part zeroed), ws_tile its inverse,
+// *flag_out the refinement flag, *info_b the first bad pivot (if none was recorded before).
+__device__ __forceinline__ void diag_factor_tile(unsigned char* smem_raw, double* __restrict__ Atile, int64_t lda,
+                                                 int kb, int64_t j0, double* __restrict__ ws,
+                                                 double* __restrict__ flag_out, int32_t* __restrict__ info_b) {
   double* Ls = reinterpret_cast<double*>(smem_raw);
   double* Inv = Ls + TILE * DLD;
   double* rdiag = Inv + NINV * 32 * ILD;
   int* s_bad = reinterpret_cast<int*>(rdiag + TILE);
-
-  const int b = blockIdx.x;
-  A += (int64_t)b * strideA;
-  double* flags = ws + (int64_t)b * strideWs + (int64_t)nt_total * TILE * TILE;
-  ws += (int64_t)b * strideWs + (int64_t)kt * TILE * TILE;
-  const int64_t j0 = (int64_t)kt * TILE;
-  const int kb = static_cast<int>(min64(TILE, n - j0));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
 
   for (int idx = tid; idx < TILE * TILE; idx += 256) {
     const int r = idx >> 7, c = idx & 127;
     double v = (r == c) ? 1.0 : 0.0;
-    if (r < kb && c <= r) v = A[(j0 + r) * lda + j0 + c];
+    if (r < kb && c <= r) v = __ldcg(Atile + (int64_t)r * lda + c);
     Ls[r * DLD + c] = v;
   }
   if (tid == 0) *s_bad = 0;
@@ -285,16 +282,28 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, 
       mI = fmax(mI, red[8 + i]);
     }
     const double kappa = mL * mI;
-    flags[kt] = (kappa > REFINE_KAPPA || !(kappa == kappa)) ? 1.0 : 0.0;
+    *flag_out = (kappa > REFINE_KAPPA || !(kappa == kappa)) ? 1.0 : 0.0;
   }
   for (int idx = tid; idx < TILE * TILE; idx += 256) {
     const int r = idx >> 7, c = idx & 127;
-    if (r < kb && c < kb) A[(j0 + r) * lda + j0 + c] = (c <= r) ? Ls[r * DLD + c] : 0.0;
+    if (r < kb && c < kb) Atile[(int64_t)r * lda + c] = (c <= r) ? Ls[r * DLD + c] : 0.0;
     double v = 0.0;
     if (r < kb && c <= r) v = Inv[blk(r >> 5, c >> 5) * 32 * ILD + (r & 31) * ILD + (c & 31)];
     ws[idx] = v;
   }
-  if (tid == 0 && *s_bad != 0 && info[b] == 0) info[b] = static_cast<int32_t>(j0) + *s_bad;
+  if (tid == 0 && *s_bad != 0 && *info_b == 0) *info_b = static_cast<int32_t>(j0) + *s_bad;
+}
+
+__global__ void __launch_bounds__(256, 1)
+potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, int nt_total, int64_t n,
+                  double* __restrict__ ws, int64_t strideWs, int32_t* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int64_t j0 = (int64_t)kt * TILE;
+  const int kb = static_cast<int>(min64(TILE, n - j0));
+  double* wsb = ws + (int64_t)b * strideWs;
+  diag_factor_tile(smem_raw, A + (int64_t)b * strideA + j0 * lda + j0, lda, kb, j0, wsb + (int64_t)kt * TILE * TILE,
+                   wsb + (int64_t)nt_total * TILE * TILE + kt, info + b);
 }
 
 // --------------------------------------------------------------------------------------
@@ -431,6 +440,143 @@ trsm_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const dou
   }
 }
 
+// --------------------------------------------------------------------------------------
+// v2: persistent left-looking tile-dataflow Cholesky.  One CTA per SM pulls tile tasks (i, j)
+// from a global ticket counter in column-major order (every dependency of a task has a smaller
+// ticket, so a spinning CTA only ever waits on work that is already running or done: no
+// deadlock, no co-residency requirement).  Task (i, j):
+//     acc = sum_{k<j} L_ik L_jk^T   one long-K DMMA GEMM, waiting per 128-column block on the
+//                                   "ready" flags of the tiles it streams
+//     T   = A_ij - acc              accumulators meet the tile exactly once (HBM traffic n^2 per
+//                                   sweep instead of n^3 / (3 * 128) for the right-looking form)
+//     i == j:  L_jj = chol(T), Linv_jj, refinement flag   (diag_factor_tile)
+//     i >  j:  L_ij = T L_jj^-T                           (tile_solve, after L_jj is ready)
+// Appended row tiles (B) and batched matrices are just more tasks of the same list.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_ready(const int* flag) {
+  while (ld_acquire(flag) == 0) __nanosleep(40);
+}
+
+// gemm_nt_mainloop over K = 128 * ktiles with per-k-tile dependency waits on readyA[kt], readyB[kt].
+__device__ __forceinline__ void gemm_nt_mainloop_dep(GemmStage* stages, const double* __restrict__ Ap, int64_t lda,
+                                                     int validA, const double* __restrict__ Bp, int64_t ldb,
+                                                     int validB, int K, Acc& acc, const int* readyA,
+                                                     const int* readyB) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
+  const int nchunks = K / BK;
+  constexpr int CPT = TILE / BK;  // chunks per k-tile
+  auto issue = [&](int nc) {
+    if (nc % CPT == 0) {
+      wait_ready(readyA + nc / CPT);
+      if (readyB != readyA) wait_ready(readyB + nc / CPT);
+    }
+    load_chunk(stages[nc % STAGES], Ap, lda, validA, Bp, ldb, validB, nc * BK, K);
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nchunks) issue(s);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    mma_chunk(stages[c % STAGES], acc, wm, wn, gid, tig);
+    const int nc = c + STAGES - 1;
+    if (nc < nchunks) issue(nc);
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+constexpr size_t DF_SMEM_BYTES = DIAG_SMEM_BYTES > GEMM_SMEM_BYTES ? DIAG_SMEM_BYTES : GEMM_SMEM_BYTES;
+constexpr int DF_POOL_TILES = 192;  // scratch tiles for the persistent grid (>= SM count)
+
+struct DfArgs {
+  double* A; int64_t lda; int64_t n; int64_t strideA;
+  double* B; int64_t ldb; int64_t nb; int64_t strideB;
+  int batch; int nt; int nbt; int total_tasks;
+  double* ws; int64_t strideWs;   // per matrix: inverse tiles, refine flags (see ws_* helpers)
+  double* pool;                   // gridDim.x scratch tiles
+  int32_t* info;
+  int* ticket; int* ready;        // ready[(b * (nt + nbt) + i) * nt + j]
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const DfArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_task;
+  GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int rows_total = p.nt + p.nbt;
+  double* scratch = p.pool + (int64_t)blockIdx.x * TILE * TILE;
+  for (;;) {
+    if (tid == 0) s_task = atomicAdd(p.ticket, 1);
+    __syncthreads();
+    const int t = s_task;
+    __syncthreads();
+    if (t >= p.total_tasks) break;
+    // decode ticket -> (column j, matrix b, row tile i); columns outermost, diagonal task first
+    int j = 0, rem = t;
+    for (;; ++j) {
+      const int per_col = p.batch * (rows_total - j);
+      if (rem < per_col) break;
+      rem -= per_col;
+    }
+    const int rows_in_col = rows_total - j;
+    const int b = rem / rows_in_col;
+    const int i = j + rem % rows_in_col;
+
+    double* Ab = p.A + (int64_t)b * p.strideA;
+    const int kb = static_cast<int>(min64(TILE, p.n - (int64_t)j * TILE));
+    const double* rowj = Ab + (int64_t)j * TILE * p.lda;
+    double* rowi;
+    int64_t ldi;
+    int valid;
+    if (i < p.nt) {
+      rowi = Ab + (int64_t)i * TILE * p.lda; ldi = p.lda;
+      valid = static_cast<int>(min64(TILE, p.n - (int64_t)i * TILE));
+    } else {
+      rowi = p.B + (int64_t)b * p.strideB + (int64_t)(i - p.nt) * TILE * p.ldb; ldi = p.ldb;
+      valid = static_cast<int>(min64(TILE, p.nb - (int64_t)(i - p.nt) * TILE));
+    }
+    int* ready_b = p.ready + (int64_t)b * rows_total * p.nt;
+    const int* ready_i = ready_b + (int64_t)i * p.nt;
+    const int* ready_j = ready_b + (int64_t)j * p.nt;
+    double* wsb = p.ws + (int64_t)b * p.strideWs;
+    double* T = rowi + (int64_t)j * TILE;
+
+    if (j > 0) {
+      Acc acc;
+      acc_zero(acc);
+      gemm_nt_mainloop_dep(stages, rowi, ldi, valid, rowj, p.lda, kb, j * TILE, acc, ready_i, ready_j);
+      store_tile<1>(T, ldi, valid, kb, acc, i == j);
+      __threadfence();
+      __syncthreads();
+    }
+    if (i == j) {
+      diag_factor_tile(smem_raw, T, p.lda, kb, (int64_t)j * TILE, wsb + (int64_t)j * TILE * TILE,
+                       wsb + (int64_t)p.nt * TILE * TILE + j, p.info + b);
+    } else {
+      wait_ready(ready_j + j);
+      const bool refine = __ldcg(wsb + (int64_t)p.nt * TILE * TILE + j) != 0.0;
+      tile_solve(stages, T, ldi, valid, kb, wsb + (int64_t)j * TILE * TILE, rowj + (int64_t)j * TILE, p.lda, refine,
+                 scratch);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release(ready_b + (int64_t)i * p.nt + j, 1);
+  }
+}
+
 static void set_smem_attrs() {
   static bool done = false;
   if (done) return;
@@ -438,6 +584,7 @@ static void set_smem_attrs() {
   cudaFuncSetAttribute(trsm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
   cudaFuncSetAttribute(gemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
   cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
+  cudaFuncSetAttribute(potrf_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM_BYTES);
   done = true;
 }
 
@@ -451,10 +598,15 @@ static int64_t ws_flags_off(int64_t nt) { return nt * TILE * TILE; }
 static int64_t ws_scratch_off(int64_t nt) { return nt * TILE * TILE + ((nt + 1) & ~(int64_t)1); }
 static int64_t ws_stride(int64_t nt, int64_t nbt) { return ws_scratch_off(nt) + (nt + nbt) * TILE * TILE; }
 
+// After the per-matrix regions: [DF_POOL_TILES scratch tiles][int region: ticket (2 ints) + ready flags].
+static int64_t ws_ready_ints(int64_t nt, int64_t nbt, int64_t batch) { return 2 + batch * (nt + nbt) * nt; }
+
 extern "C" size_t gpar_potrf_workspace_bytes(int64_t n, int64_t nb, int64_t batch) {
   if (n <= 0 || batch <= 0) return 0;
   const int64_t nt = (n + TILE - 1) / TILE, nbt = nb > 0 ? (nb + TILE - 1) / TILE : 0;
-  return (size_t)batch * (size_t)ws_stride(nt, nbt) * sizeof(double);
+  const int64_t doubles = batch * ws_stride(nt, nbt) + (int64_t)DF_POOL_TILES * TILE * TILE +
+                          (ws_ready_ints(nt, nbt, batch) + 1) / 2 + 2;
+  return (size_t)doubles * sizeof(double);
 }
 
 extern "C" size_t gpar_trsm_rows_scratch_bytes(int64_t nb) {
@@ -486,6 +638,33 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
   const int nbt = nb > 0 ? (int)((nb + TILE - 1) / TILE) : 0;
   const int64_t strideWs = ws_stride(nt, nbt);
   double* scratch = ws + ws_scratch_off(nt);
+  static const bool use_v1 = (getenv("GPAR_POTRF_V1") != nullptr);
+  if (!use_v1) {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    DfArgs p;
+    p.A = A; p.lda = lda; p.n = n; p.strideA = strideA;
+    p.B = B; p.ldb = ldb; p.nb = nb; p.strideB = strideB;
+    p.batch = (int)batch; p.nt = nt; p.nbt = nbt;
+    int64_t total = 0;
+    for (int j = 0; j < nt; ++j) total += batch * (int64_t)(nt + nbt - j);
+    if (total > 0x7fffffff) { set_error("gpar_potrf: too many tile tasks"); return -9; }
+    p.total_tasks = (int)total;
+    p.ws = ws; p.strideWs = strideWs;
+    p.pool = ws + batch * strideWs;
+    p.info = info;
+    int* ints = reinterpret_cast<int*>(p.pool + (int64_t)DF_POOL_TILES * TILE * TILE);
+    p.ticket = ints; p.ready = ints + 2;
+    cudaMemsetAsync(ints, 0, sizeof(int) * (size_t)ws_ready_ints(nt, nbt, batch), stream);
+    int grid = num_sms < DF_POOL_TILES ? num_sms : DF_POOL_TILES;
+    if ((int64_t)grid > total) grid = (int)total;
+    potrf_dataflow_kernel<<<grid, GEMM_THREADS, DF_SMEM_BYTES, stream>>>(p);
+    return check_launch("gpar_potrf");
+  }
   for (int k = 0; k < nt; ++k) {
     const int64_t j0 = (int64_t)k * TILE;
     const int kb = (int)((n - j0 < TILE) ? (n - j0) : TILE);

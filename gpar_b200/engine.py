@@ -6,6 +6,7 @@ torch is plumbing only (device memory, streams, host<->device copies); every
 arithmetic step on the hot path is one of our sm_100a kernels."""
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -93,7 +94,10 @@ class Engine:
                                  strideB, batch, self.addr(ws), C.c_void_p(info.data_ptr()), self.stream)
         check(rc, "gpar_potrf")
         nt = (n + TILE - 1) // TILE
-        self.launches += nt + max(nt - 1, 0) + (nt if nb > 0 else max(nt - 1, 0))
+        if os.environ.get("GPAR_POTRF_V1"):
+            self.launches += nt + max(nt - 1, 0) + (nt if nb > 0 else max(nt - 1, 0))
+        else:
+            self.launches += 1  # one persistent dataflow kernel
         self.flops += batch * (n ** 3 / 3.0 + nb * float(n) ** 2)
         self._infos.append(info)
         return ws, info
