@@ -77,6 +77,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
                : "memory");
 }
 
+// Warp index broadcast from lane 0: tells the compiler the value is warp-uniform, which keeps
+// branches on it (role dispatch, triangular skipping) free of WARPSYNC / BSSY divergence code.
+__device__ __forceinline__ int canonical_warp() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
+
 // ---- warp reductions -------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -18,292 +18,311 @@ namespace gpar {
 // --------------------------------------------------------------------------------------
 // Diagonal tile: factor + invert, entirely in shared memory.
 // --------------------------------------------------------------------------------------
-constexpr int DLD = 129;  // row stride of the tile in shared memory
-constexpr int ILD = 33;   // row stride of a 32x32 inverse block
-constexpr int NB32 = TILE / 32;
-constexpr int NINV = NB32 * (NB32 + 1) / 2;  // 10 lower blocks
+constexpr int DLD = 132;  // row stride of the tile in shared memory: = 4 (mod 16) doubles makes the DMMA
+                          // fragment loads bank-conflict free; rows stay 16-byte aligned for cp.async
 constexpr double REFINE_KAPPA = 1.0e3;  // kappa_inf(L_kk) above which the tile solves are refined
-constexpr size_t DIAG_SMEM_BYTES = sizeof(double) * (TILE * DLD + NINV * 32 * ILD + TILE) + 16;
+constexpr size_t DIAG_SMEM_BYTES = sizeof(double) * (TILE * DLD + TILE + 32) + 16;
 
-__device__ __forceinline__ int blk(int b, int a) { return b * (b + 1) / 2 + a; }
-
-// Warp-level Cholesky of the 32x32 block at Ls (row stride DLD).  Lane r owns row r in
-// registers; finished rows are broadcast through shared memory.  Returns the 1-based index of
-// the first non-positive pivot (0 if none) in every lane.
-__device__ __forceinline__ int potf2_32(double* Ls, double* rdiag, int lane) {
-  double a[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? Ls[lane * DLD + c] : 0.0;
-  int bad = 0;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int t = 0; t + 3 < c; t += 4) {
-      s0 = fma(a[t], Ls[c * DLD + t], s0);
-      s1 = fma(a[t + 1], Ls[c * DLD + t + 1], s1);
-      s2 = fma(a[t + 2], Ls[c * DLD + t + 2], s2);
-      s3 = fma(a[t + 3], Ls[c * DLD + t + 3], s3);
-    }
-#pragma unroll
-    for (int t = (c / 4) * 4; t < c; ++t) s0 = fma(a[t], Ls[c * DLD + t], s0);
-    const double v = a[c] - ((s0 + s1) + (s2 + s3));
-    double piv = __shfl_sync(0xffffffffu, v, c);
-    if (!(piv > 0.0)) {
-      if (bad == 0) bad = c + 1;
-      piv = 1.0;
-    }
-    const double rs = rsqrt(piv);
-    const double l = (lane == c) ? piv * rs : v * rs;
-    a[c] = l;
-    if (lane >= c) Ls[lane * DLD + c] = l;
-    if (lane == c) rdiag[c] = rs;
-    __syncwarp();
-  }
-  return bad;
-}
-
-// Warp-level inverse of the lower-triangular 32x32 block at Ls: lane j solves L x = e_j.
-__device__ __forceinline__ void trtri_32(const double* Ls, const double* rdiag, double* inv, int lane) {
-  double x[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int k = 0; k + 3 < i; k += 4) {
-      s0 = fma(-Ls[i * DLD + k], x[k], s0);
-      s1 = fma(-Ls[i * DLD + k + 1], x[k + 1], s1);
-      s2 = fma(-Ls[i * DLD + k + 2], x[k + 2], s2);
-      s3 = fma(-Ls[i * DLD + k + 3], x[k + 3], s3);
-    }
-#pragma unroll
-    for (int k = (i / 4) * 4; k < i; ++k) s0 = fma(-Ls[i * DLD + k], x[k], s0);
-    x[i] = ((s0 + s1) + (s2 + s3)) * rdiag[i];
-  }
-#pragma unroll
-  for (int i = 0; i < 32; ++i) inv[i * ILD + lane] = x[i];
-}
-
-// acc[t] += sum_k A(gid, k0+tig) * B(k0+tig, t*8+gid) over K (multiple of 4): one 8 x (8*NTN) strip.
-template <int NTN, class FA, class FB>
-__device__ __forceinline__ void strip_mma(double (&c)[NTN][2], int K, FA a, FB b, int gid, int tig) {
-  for (int k0 = 0; k0 < K; k0 += 4) {
-    const double av = a(gid, k0 + tig);
-#pragma unroll
-    for (int t = 0; t < NTN; ++t) {
-      const double bv = b(k0 + tig, t * 8 + gid);
-      dmma884(c[t][0], c[t][1], av, bv);
-    }
-  }
-}
-
-// Factor one diagonal tile in shared memory (all 256 threads of the CTA): Atile points at
-// A[j0][j0]; on return the tile holds L_kk (strictly upper part zeroed), ws_tile its inverse,
+// Factor one diagonal tile in shared memory (all 256 threads of the CTA).  Atile points at
+// A[j0][j0]; on return the tile holds L_kk (strictly upper part zeroed), ws its inverse,
 // *flag_out the refinement flag, *info_b the first bad pivot (if none was recorded before).
+//
+// Right-looking sweep over 16 column blocks of width 8 on ONE 128 x 129 shared array:
+//   lower triangle  = L (in place);
+//   strict upper    = the appended identity rows of the sweep, i.e. (I L^-T)[r][c] = Linv[c][r]
+//                     (the diagonal of Linv is rdiag = 1 / L_rr), so the inverse costs no extra
+//                     phase and no extra storage.
+// Per block: (a) warps 0-3: every thread factors the 8x8 diagonal block redundantly in registers
+// (chain = 8 x (rsqrt + mul + fma), no communication), (b) thread r solves row r against it by
+// substitution (backward stable: no refinement needed), (c) all warps apply the rank-8 trailing
+// update with DMMA (independent 8x8 sub-tiles, no accumulate chains).
 __device__ __forceinline__ void diag_factor_tile(unsigned char* smem_raw, double* __restrict__ Atile, int64_t lda,
                                                  int kb, int64_t j0, double* __restrict__ ws,
-                                                 double* __restrict__ flag_out, int32_t* __restrict__ info_b) {
+                                                 double* __restrict__ flag_out, int32_t* __restrict__ info_b,
+                                                 long long* prof = nullptr) {
+#define GPAR_PROF(i) do { if (prof && threadIdx.x == 0) prof[i] = clock64(); } while (0)
+  GPAR_PROF(0);
   double* Ls = reinterpret_cast<double*>(smem_raw);
-  double* Inv = Ls + TILE * DLD;
-  double* rdiag = Inv + NINV * 32 * ILD;
-  int* s_bad = reinterpret_cast<int*>(rdiag + TILE);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  double* rdiag = Ls + TILE * DLD;
+  double* red = rdiag + TILE;  // 32 doubles of reduction scratch
+  int* s_bad = reinterpret_cast<int*>(red + 32);
+  const int tid = threadIdx.x, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  const int warp = canonical_warp();
 
-  for (int idx = tid; idx < TILE * TILE; idx += 256) {
-    const int r = idx >> 7, c = idx & 127;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < kb && c <= r) v = __ldcg(Atile + (int64_t)r * lda + c);
-    Ls[r * DLD + c] = v;
-  }
-  if (tid == 0) *s_bad = 0;
-  __syncthreads();
-
-  for (int a = 0; a < NB32; ++a) {
-    const int o = 32 * a;
-    if (warp == 0) {
-      int bad = potf2_32(Ls + o * DLD + o, rdiag + o, lane);
-      if (bad && lane == 0 && *s_bad == 0) *s_bad = o + bad;
-      __syncwarp();
-      trtri_32(Ls + o * DLD + o, rdiag + o, Inv + blk(a, a) * 32 * ILD, lane);
-    }
-    __syncthreads();
-    const int rem = TILE - (o + 32);
-    if (rem == 0) break;
-    // panel: X = T L_aa^-T, T = rows [o+32, 128) x cols [o, o+32) (in place, a warp owns whole rows).
-    // X0 = T inv^T, then one step of iterative refinement against L_aa itself
-    // (R = T - X0 L_aa^T, X = X0 + R inv^T) so that the solve stays backward stable when the
-    // block is ill-conditioned (explicit inverses alone lose a factor cond(L_aa)).
-    {
-      const double* inv = Inv + blk(a, a) * 32 * ILD;
-      const double* Laa = Ls + o * DLD + o;
-      for (int strip = warp; strip < rem / 8; strip += 8) {
-        double* T = Ls + (o + 32 + strip * 8) * DLD + o;
-        auto fa = [&](int m, int k) { return T[m * DLD + k]; };
-        auto finv = [&](int k, int nn) { return inv[nn * ILD + k]; };
-        auto flt = [&](int k, int nn) { return (k <= nn) ? Laa[nn * DLD + k] : 0.0; };
-        double t0[4][2], x0[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          t0[t][0] = T[gid * DLD + t * 8 + 2 * tig];
-          t0[t][1] = T[gid * DLD + t * 8 + 2 * tig + 1];
-        }
-        strip_mma<4>(x0, 32, fa, finv, gid, tig);
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          T[gid * DLD + t * 8 + 2 * tig] = x0[t][0];
-          T[gid * DLD + t * 8 + 2 * tig + 1] = x0[t][1];
-        }
-        __syncwarp();
-        double xl[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-        strip_mma<4>(xl, 32, fa, flt, gid, tig);
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          T[gid * DLD + t * 8 + 2 * tig] = t0[t][0] - xl[t][0];
-          T[gid * DLD + t * 8 + 2 * tig + 1] = t0[t][1] - xl[t][1];
-        }
-        __syncwarp();
-        strip_mma<4>(x0, 32, fa, finv, gid, tig);  // x0 += R inv^T
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          T[gid * DLD + t * 8 + 2 * tig] = x0[t][0];
-          T[gid * DLD + t * 8 + 2 * tig + 1] = x0[t][1];
-        }
+  // ---- load the lower triangle with cp.async (16-byte, all in flight), then fix up: zeros above
+  // the diagonal, identity padding beyond kb ------------------------------------------------------
+  {
+    const bool vec_ok = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(Atile) & 15) == 0);
+    if (vec_ok) {
+      // zero-filling copies: 16 B below the diagonal, 8 B on it, 0 B (pure zero fill) above / beyond kb
+#pragma unroll 8
+      for (int q = 0; q < 32; ++q) {
+        const int idx = tid + q * 256;  // 0..8191: row r, double2 column c
+        const int r = idx >> 6, c = (idx & 63) * 2;
+        const int bytes = (r < kb) ? ((c + 1 <= r) ? 16 : ((c == r) ? 8 : 0)) : 0;
+        cp_async16(&Ls[r * DLD + c], bytes ? (Atile + (int64_t)r * lda + c) : Atile, bytes);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+    } else {
+      for (int idx = tid; idx < TILE * TILE; idx += 256) {
+        const int r = idx >> 7, c = idx & 127;
+        Ls[r * DLD + c] = (r < kb && c <= r) ? __ldcg(Atile + (int64_t)r * lda + c) : 0.0;
       }
     }
     __syncthreads();
-    // trailing: T2[m][nn] -= sum_k X[m][k] X[nn][k], lower 8x8 tiles only
-    {
-      const double* X = Ls + (o + 32) * DLD + o;
-      double* T2 = Ls + (o + 32) * DLD + (o + 32);
-      const int ntm = rem / 8;
-      // work units: (tm, group g of 4 column tiles) with 4*g <= tm
-      int unit = 0;
-      for (int tm = 0; tm < ntm; ++tm) {
-        for (int g = 0; g * 4 <= tm; ++g, ++unit) {
-          if ((unit & 7) != warp) continue;
-          double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-          const double* Xa = X + (tm * 8) * DLD;
-          const double* Xb = X + (g * 32) * DLD;
-          strip_mma<4>(
-              c, 32, [&](int m, int k) { return Xa[m * DLD + k]; }, [&](int k, int nn) { return Xb[nn * DLD + k]; },
-              gid, tig);
+    if (tid >= kb && tid < TILE) Ls[tid * DLD + tid] = 1.0;  // identity padding
+  }
+  if (tid == 0) *s_bad = 0;
+  __syncthreads();
+  GPAR_PROF(1);
+
+  // Warp 0: factor the 8x8 diagonal block kblk in registers (all lanes redundantly: the chain is
+  // 8 x (rsqrt + mul + fma) with no communication); lanes 0-7 publish row m of L8 and 1 / L_mm.
+  auto factor_block = [&](int kblk) {
+    const int c0 = 8 * kblk;
+    double d[8][8], rd[8];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int col = g * 32 + t * 8 + 2 * tig;
-            if (g * 4 + t <= tm) {
-              double* p = T2 + (tm * 8 + gid) * DLD + col;
-              p[0] -= c[t][0];
-              p[1] -= c[t][1];
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) d[i][j] = Ls[(c0 + i) * DLD + c0 + j];
+    int bad = 0;
+    if (kblk == 1) GPAR_PROF(13);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double piv = d[j][j];
+      if (!(piv > 0.0)) {
+        if (bad == 0) bad = j + 1;
+        piv = 1.0;
+      }
+      const double rs = rsqrt(piv);
+      rd[j] = rs;
+      d[j][j] = piv * rs;
+#pragma unroll
+      for (int i = j + 1; i < 8; ++i) d[i][j] *= rs;
+#pragma unroll
+      for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+        for (int l = j + 1; l <= i; ++l) d[i][l] = fma(-d[i][j], d[l][j], d[i][l]);
+    }
+    if (kblk == 1) GPAR_PROF(14);
+    // publish without divergent branches: predicated stores, lane mm writes row mm
+#pragma unroll
+    for (int mm = 0; mm < 8; ++mm) {
+#pragma unroll
+      for (int j = 0; j <= mm; ++j) {
+        const double v = d[mm][j];
+        if (lane == mm) Ls[(c0 + mm) * DLD + c0 + j] = v;
+      }
+      const double rv = rd[mm];
+      if (lane == mm) rdiag[c0 + mm] = rv;
+    }
+    if (bad && lane == 0 && *s_bad == 0) *s_bad = c0 + bad;
+  };
+
+  if (warp == 0) factor_block(0);
+#pragma unroll 1
+  for (int k = 0; k < TILE / 8; ++k) {
+    const int c0 = 8 * k;
+    __syncthreads();  // L8(k) published; trailing update of step k-1 complete
+    if (k == 0 || k == 8) GPAR_PROF(2 + (k ? 6 : 0));
+    if (warp < 4) {
+      // row r = tid: x L8^T = t by substitution against the published block (backward stable)
+      double d[8][8], rd[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        rd[i] = rdiag[c0 + i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) d[i][j] = Ls[(c0 + i) * DLD + c0 + j];
+      }
+      const int r = tid;
+      const bool in_block = (r >= c0 && r < c0 + 8);
+      double x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = in_block ? ((r - c0 == j) ? 1.0 : 0.0) : Ls[r * DLD + c0 + j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        double sacc = x[j];
+#pragma unroll
+        for (int i = 0; i < j; ++i) sacc = fma(-x[i], d[j][i], sacc);
+        x[j] = sacc * rd[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)  // in-block rows keep L8 in their lower part: only the strict upper is theirs
+        if (!in_block || j > r - c0) Ls[r * DLD + c0 + j] = x[j];
+    }
+    if (k == 0 || k == 8) GPAR_PROF(3 + (k ? 6 : 0));
+    __syncthreads();
+    if (k == 0 || k == 8) GPAR_PROF(4 + (k ? 6 : 0));
+    if (k == TILE / 8 - 1) break;
+    // rank-8 trailing update C -= X X^T.  Column tile ct > k meets row tiles rt in [0, k] (inverse
+    // rows, strict-upper region) and rt in [ct, 15] (L rows).  Warp 0 takes the next diagonal
+    // sub-tile and factors it right away (look-ahead); warps 1-7 share the other row tiles and
+    // process four column tiles at a time (independent accumulators).
+    if (warp == 0) {
+      const int row = (k + 1) * 8 + gid;
+      const double a0 = Ls[row * DLD + c0 + tig], a1 = Ls[row * DLD + c0 + 4 + tig];
+      double* pc = Ls + row * DLD + (k + 1) * 8 + 2 * tig;
+      double c0v = pc[0], c1v = pc[1];
+      dmma884(c0v, c1v, -a0, a0);
+      dmma884(c0v, c1v, -a1, a1);
+      if (2 * tig <= gid) pc[0] = c0v;
+      if (2 * tig + 1 <= gid) pc[1] = c1v;
+      __syncwarp();
+      if (k == 0 || k == 8) GPAR_PROF(5 + (k ? 6 : 0));
+      factor_block(k + 1);
+      if (k == 0 || k == 8) GPAR_PROF(6 + (k ? 6 : 0));
+    } else {
+      if (prof && k == 0 && tid == 32) prof[15] = clock64();
+      int unit = 0;
+      for (int rt = 0; rt < TILE / 8; ++rt) {
+        if (rt == k + 1) continue;
+        const int ct_lo = k + 1, ct_hi = (rt <= k) ? (TILE / 8 - 1) : rt;  // inclusive
+        const int nunits = (ct_hi - ct_lo + 4) / 4;
+        // does this warp own any (rt, batch) unit?  units are dealt round-robin to warps 1..7
+        const int first = (warp - 1 - unit % 7 + 7) % 7;  // offset of my first unit within this row tile
+        const int ubase = unit;
+        unit += nunits;
+        if (first >= nunits) continue;
+        (void)ubase;
+        const int row = rt * 8 + gid;
+        double a0, a1;
+        if (rt == k) {  // inverse rows of the current block: strict upper stored, diagonal = rdiag
+          a0 = (tig > gid) ? Ls[row * DLD + c0 + tig] : ((tig == gid) ? rdiag[row] : 0.0);
+          a1 = (tig + 4 > gid) ? Ls[row * DLD + c0 + 4 + tig] : ((tig + 4 == gid) ? rdiag[row] : 0.0);
+        } else {
+          a0 = Ls[row * DLD + c0 + tig];
+          a1 = Ls[row * DLD + c0 + 4 + tig];
+        }
+        a0 = -a0;
+        a1 = -a1;
+        for (int ctb = ct_lo + 4 * first; ctb <= ct_hi; ctb += 28) {
+          double b0[4], b1[4], cv[4][2];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int ct = min(ctb + u, ct_hi);
+            b0[u] = Ls[(ct * 8 + gid) * DLD + c0 + tig];
+            b1[u] = Ls[(ct * 8 + gid) * DLD + c0 + 4 + tig];
+            const double* pc = Ls + row * DLD + ct * 8 + 2 * tig;
+            cv[u][0] = pc[0];
+            cv[u][1] = pc[1];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma884(cv[u][0], cv[u][1], a0, b0[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma884(cv[u][0], cv[u][1], a1, b1[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int ct = ctb + u;
+            if (ct > ct_hi) continue;
+            double* pc = Ls + row * DLD + ct * 8 + 2 * tig;
+            if (rt == ct) {  // diagonal sub-tile: its strict upper part belongs to the inverse rows
+              if (2 * tig <= gid) pc[0] = cv[u][0];
+              if (2 * tig + 1 <= gid) pc[1] = cv[u][1];
+            } else {
+              pc[0] = cv[u][0];
+              pc[1] = cv[u][1];
             }
           }
         }
       }
+      if (prof && k == 0 && tid == 32) prof[16] = clock64();
     }
-    __syncthreads();
   }
+  GPAR_PROF(19);
 
-  // ---- assemble the off-diagonal blocks of the inverse, block row by block row --------------
-  for (int bb = 1; bb < NB32; ++bb) {
-    // stage 1: M_ba = sum_{c=a}^{bb-1} L[bb][c] Inv[c][a]  -> stored in Inv[bb][a]
-    for (int unit = warp; unit < bb * 4; unit += 8) {
-      const int a = unit >> 2, tm = unit & 3;
-      double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-      for (int cc = a; cc < bb; ++cc) {
-        const double* Lb = Ls + (32 * bb + tm * 8) * DLD + 32 * cc;
-        const double* Ic = Inv + blk(cc, a) * 32 * ILD;
-        strip_mma<4>(
-            c, 32, [&](int m, int k) { return Lb[m * DLD + k]; }, [&](int k, int nn) { return Ic[k * ILD + nn]; }, gid,
-            tig);
-      }
-      double* M = Inv + blk(bb, a) * 32 * ILD + (tm * 8) * ILD;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        M[gid * ILD + t * 8 + 2 * tig] = c[t][0];
-        M[gid * ILD + t * 8 + 2 * tig + 1] = c[t][1];
-      }
-    }
-    __syncthreads();
-    // stage 2: Inv[bb][a] = -Inv[bb][bb] M_ba, in place: a warp owns 8 whole columns.
-    for (int unit = warp; unit < bb * 4; unit += 8) {
-      const int a = unit >> 2, tn = unit & 3;
-      double* M = Inv + blk(bb, a) * 32 * ILD + tn * 8;
-      const double* Ib = Inv + blk(bb, bb) * 32 * ILD;
-      double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-      // out[m][nn] over 4 row tiles: treat row tiles as the "N" strips by transposing roles:
-      // out^T[nn][m] = sum_k M^T[nn][k] Ib^T[k][m]  -> A(nn,k) = M[k][nn], B(k,m) = Ib[m][k]
-      strip_mma<4>(
-          c, 32, [&](int nn, int k) { return M[k * ILD + nn]; }, [&](int k, int m) { return Ib[m * ILD + k]; }, gid,
-          tig);
-      __syncwarp();
-      // c[t][e] = out^T[gid][t*8 + 2*tig + e] = out[m = t*8+2*tig+e][nn = gid]
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        M[(t * 8 + 2 * tig) * ILD + gid] = -c[t][0];
-        M[(t * 8 + 2 * tig + 1) * ILD + gid] = -c[t][1];
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- write back L (valid block; its strictly upper part is zeroed so the tile can serve as a
-  // GEMM operand) and Linv (dense 128x128, zero padded); kappa_inf(L_kk) decides refinement -----
-  double rowL = 0.0, rowI = 0.0;  // thread t < 128 accumulates the abs row sums of row t
-  if (tid < kb) {
-    for (int c = 0; c <= tid; ++c) {
-      rowL += fabs(Ls[tid * DLD + c]);
-      rowI += fabs(Inv[blk(tid >> 5, c >> 5) * 32 * ILD + (tid & 31) * ILD + (c & 31)]);
-    }
-  }
-  // max over the block via shared memory (reuse rdiag as scratch after a barrier)
-  __syncthreads();
-  double* red = rdiag;
-  if (tid < TILE) red[tid] = 0.0;
-  __syncthreads();
+  // ---- kappa_inf(L_kk) = ||L||_inf ||Linv||_inf decides refinement: two threads per row ------
   {
-    double mL = rowL, mI = rowI;
+    const int r = tid >> 1, h = tid & 1;
+    double rowL = 0.0, rowI = 0.0;
+    if (r < kb) {
+      // row r of L: columns [0, r]; row r of Linv: Linv[r][c] = Ls[c][r] for c < r, rdiag[r] at c = r
+      const int lo = h ? (r + 1) / 2 : 0, hi = h ? r : (r + 1) / 2;
+#pragma unroll 8
+      for (int c = lo; c < hi; ++c) {
+        rowL += fabs(Ls[r * DLD + c]);
+        rowI += fabs(Ls[c * DLD + r]);
+      }
+      if (h) {
+        rowL += fabs(Ls[r * DLD + r]);
+        rowI += fabs(rdiag[r]);
+      }
+    }
+    rowL += __shfl_xor_sync(0xffffffffu, rowL, 1);
+    rowI += __shfl_xor_sync(0xffffffffu, rowI, 1);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      mL = fmax(mL, __shfl_xor_sync(0xffffffffu, mL, off));
-      mI = fmax(mI, __shfl_xor_sync(0xffffffffu, mI, off));
+    for (int off = 16; off > 1; off >>= 1) {
+      rowL = fmax(rowL, __shfl_xor_sync(0xffffffffu, rowL, off));
+      rowI = fmax(rowI, __shfl_xor_sync(0xffffffffu, rowI, off));
     }
     if (lane == 0) {
-      red[warp] = mL;
-      red[8 + warp] = mI;
+      red[warp] = rowL;
+      red[8 + warp] = rowI;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double mL = 0.0, mI = 0.0;
+      for (int i = 0; i < 8; ++i) {
+        mL = fmax(mL, red[i]);
+        mI = fmax(mI, red[8 + i]);
+      }
+      const double kappa = mL * mI;
+      *flag_out = (kappa > REFINE_KAPPA || !(kappa == kappa)) ? 1.0 : 0.0;
     }
   }
-  __syncthreads();
-  if (tid == 0) {
-    double mL = 0.0, mI = 0.0;
-    for (int i = 0; i < 8; ++i) {
-      mL = fmax(mL, red[i]);
-      mI = fmax(mI, red[8 + i]);
+  // ---- write back L and Linv (row major, ld = 128).  Only the lower triangles are stored, plus
+  // zeros in the strictly upper part of each 32x32 diagonal block: every consumer (MODE 2 GEMMs
+  // skip whole 32-column halves per k-chunk, backsolve starts at the 8x8 diagonal block) stays
+  // inside that region, so nothing else is ever read. -----------------------------------------------
+  {
+    const bool vec_ok = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(Atile) & 15) == 0);
+#pragma unroll 4
+    for (int idx = tid; idx < TILE * (TILE / 2); idx += 256) {  // L: row-wise, conflict free
+      const int r = idx >> 6, c = (idx & 63) * 2;
+      if (r >= kb || c > (r | 31) || c >= kb) continue;  // keep zeros in the 32x32 diagonal blocks
+      double2 lv = make_double2(0.0, 0.0);
+      if (c <= r) lv.x = Ls[r * DLD + c];
+      if (c + 1 <= r) lv.y = Ls[r * DLD + c + 1];
+      double* dst = Atile + (int64_t)r * lda + c;
+      if (vec_ok && c + 1 < kb) {
+        *reinterpret_cast<double2*>(dst) = lv;
+      } else {
+        dst[0] = lv.x;
+        if (c + 1 < kb) dst[1] = lv.y;
+      }
     }
-    const double kappa = mL * mI;
-    *flag_out = (kappa > REFINE_KAPPA || !(kappa == kappa)) ? 1.0 : 0.0;
-  }
-  for (int idx = tid; idx < TILE * TILE; idx += 256) {
-    const int r = idx >> 7, c = idx & 127;
-    if (r < kb && c < kb) Atile[(int64_t)r * lda + c] = (c <= r) ? Ls[r * DLD + c] : 0.0;
-    double v = 0.0;
-    if (r < kb && c <= r) v = Inv[blk(r >> 5, c >> 5) * 32 * ILD + (r & 31) * ILD + (c & 31)];
-    ws[idx] = v;
+    // Linv[r][c] = Ls[c][r] (c < r): transposed read.  A warp moves an 8 (r) x 4 (c) block per step
+    // with lanes laid out so that (4 c + r) mod 16 is distinct within each half warp (conflict free
+    // at stride 132); the 4 consecutive c of a row form one 32-byte sector of the output.
+    {
+      const int rr = (lane & 3) + 4 * (lane >> 4), cc = (lane >> 2) & 3;
+#pragma unroll 4
+      for (int blk = warp; blk < (TILE / 8) * (TILE / 4); blk += 8) {
+        const int R0 = (blk >> 5) * 8, C0 = (blk & 31) * 4;
+        if (C0 > (R0 | 31)) continue;
+        const int r = R0 + rr, c = C0 + cc;
+        if (r >= kb) continue;
+        double v = 0.0;
+        if (c < r) v = Ls[c * DLD + r]; else if (c == r) v = rdiag[r];
+        ws[r * TILE + c] = v;
+      }
+    }
   }
   if (tid == 0 && *s_bad != 0 && *info_b == 0) *info_b = static_cast<int32_t>(j0) + *s_bad;
+  GPAR_PROF(20);
+#undef GPAR_PROF
 }
 
 __global__ void __launch_bounds__(256, 1)
 potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, int nt_total, int64_t n,
-                  double* __restrict__ ws, int64_t strideWs, int32_t* __restrict__ info) {
+                  double* __restrict__ ws, int64_t strideWs, int32_t* __restrict__ info, long long* prof) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x;
   const int64_t j0 = (int64_t)kt * TILE;
   const int kb = static_cast<int>(min64(TILE, n - j0));
   double* wsb = ws + (int64_t)b * strideWs;
   diag_factor_tile(smem_raw, A + (int64_t)b * strideA + j0 * lda + j0, lda, kb, j0, wsb + (int64_t)kt * TILE * TILE,
-                   wsb + (int64_t)nt_total * TILE * TILE + kt, info + b);
+                   wsb + (int64_t)nt_total * TILE * TILE + kt, info + b, prof);
 }
 
 // --------------------------------------------------------------------------------------
@@ -317,7 +336,7 @@ __device__ __forceinline__ void tile_solve(GemmStage* stages, double* __restrict
                                            int64_t ldl, bool refine, double* __restrict__ scratch) {
   Acc acc;
   acc_zero(acc);
-  gemm_nt_mainloop(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);
+  gemm_nt_mainloop<2>(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);
   if (!refine) {
     store_tile<0>(T, ldt, valid, kb, acc, false);
     return;
@@ -326,12 +345,12 @@ __device__ __forceinline__ void tile_solve(GemmStage* stages, double* __restrict
   __threadfence();
   __syncthreads();
   acc_zero(acc);
-  gemm_nt_mainloop(stages, scratch, TILE, valid, Lkk, ldl, kb, kb, acc);  // X0 L_kk^T
+  gemm_nt_mainloop<2>(stages, scratch, TILE, valid, Lkk, ldl, kb, kb, acc);  // X0 L_kk^T
   store_tile<1>(T, ldt, valid, kb, acc, false);                            // T <- R = T - X0 L_kk^T
   __threadfence();
   __syncthreads();
   acc_zero(acc);
-  gemm_nt_mainloop(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);  // R Linv^T
+  gemm_nt_mainloop<2>(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);  // R Linv^T
   store_tile_add(T, ldt, scratch, TILE, valid, kb, acc);              // T <- X0 + R Linv^T
 }
 
@@ -404,7 +423,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_sub_kernel(const SubArgs
   }
   Acc acc;
   acc_zero(acc);
-  gemm_nt_mainloop(stages, Ap, lda, rows, Bp, p.ldb, cols, p.K, acc);
+  gemm_nt_mainloop<0>(stages, Ap, lda, rows, Bp, p.ldb, cols, p.K, acc);
   store_tile<1>(C, ldc, rows, cols, acc, lower_diag);
 }
 
@@ -466,13 +485,15 @@ __device__ __forceinline__ void wait_ready(const int* flag) {
 }
 
 // gemm_nt_mainloop over K = 128 * ktiles with per-k-tile dependency waits on readyA[kt], readyB[kt].
+template <int MODE>
 __device__ __forceinline__ void gemm_nt_mainloop_dep(GemmStage* stages, const double* __restrict__ Ap, int64_t lda,
                                                      int validA, const double* __restrict__ Bp, int64_t ldb,
                                                      int validB, int K, Acc& acc, const int* readyA,
                                                      const int* readyB) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = canonical_warp(), lane = threadIdx.x & 31;
   const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
   const int nchunks = K / BK;
+  const unsigned mask = block_mask<MODE>(wm, wn, validA);
   constexpr int CPT = TILE / BK;  // chunks per k-tile
   auto issue = [&](int nc) {
     if (nc % CPT == 0) {
@@ -489,7 +510,7 @@ __device__ __forceinline__ void gemm_nt_mainloop_dep(GemmStage* stages, const do
   for (int c = 0; c < nchunks; ++c) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    mma_chunk(stages[c % STAGES], acc, wm, wn, gid, tig);
+    mma_chunk<MODE>(stages[c % STAGES], acc, wm, wn, gid, tig, c * BK, mask);
     const int nc = c + STAGES - 1;
     if (nc < nchunks) issue(nc);
     cp_async_commit();
@@ -509,7 +530,14 @@ struct DfArgs {
   double* pool;                   // gridDim.x scratch tiles
   int32_t* info;
   int* ticket; int* ready;        // ready[(b * (nt + nbt) + i) * nt + j]
+  long long* prof;                // debug: globaltimer stamps of the tasks around column nt/2 (or null)
 };
+
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const DfArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -553,29 +581,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
     const int* ready_j = ready_b + (int64_t)j * p.nt;
     double* wsb = p.ws + (int64_t)b * p.strideWs;
     double* T = rowi + (int64_t)j * TILE;
+    // debug stamps: tasks (jp, jp), (jp+1, jp), (jp+1, jp+1) with jp = nt/2
+    long long* pf = nullptr;
+    if (p.prof && b == 0 && tid == 0) {
+      const int jp = p.nt / 2;
+      if (j == jp && i == jp) pf = p.prof;
+      else if (j == jp && i == jp + 1) pf = p.prof + 8;
+      else if (j == jp + 1 && i == jp + 1) pf = p.prof + 16;
+    }
+    if (pf) pf[0] = globaltimer_ns();
 
     if (j > 0) {
       Acc acc;
       acc_zero(acc);
-      gemm_nt_mainloop_dep(stages, rowi, ldi, valid, rowj, p.lda, kb, j * TILE, acc, ready_i, ready_j);
+      // (the masked lower-triangular MODE 1 path is slower than the full tile: its branches break
+      //  the DMMA/LDS software pipeline; measured 2x per chunk)
+      gemm_nt_mainloop_dep<0>(stages, rowi, ldi, valid, rowj, p.lda, kb, j * TILE, acc, ready_i, ready_j);
+      if (pf) pf[1] = globaltimer_ns();
       store_tile<1>(T, ldi, valid, kb, acc, i == j);
       __threadfence();
       __syncthreads();
+      if (pf) pf[2] = globaltimer_ns();
     }
     if (i == j) {
       diag_factor_tile(smem_raw, T, p.lda, kb, (int64_t)j * TILE, wsb + (int64_t)j * TILE * TILE,
                        wsb + (int64_t)p.nt * TILE * TILE + j, p.info + b);
     } else {
       wait_ready(ready_j + j);
+      if (pf) pf[3] = globaltimer_ns();
       const bool refine = __ldcg(wsb + (int64_t)p.nt * TILE * TILE + j) != 0.0;
       tile_solve(stages, T, ldi, valid, kb, wsb + (int64_t)j * TILE * TILE, rowj + (int64_t)j * TILE, p.lda, refine,
                  scratch);
     }
+    if (pf) pf[4] = globaltimer_ns();
     __threadfence();
     __syncthreads();
     if (tid == 0) st_release(ready_b + (int64_t)i * p.nt + j, 1);
+    if (pf) pf[5] = globaltimer_ns();
   }
 }
+
+static long long* g_df_prof = nullptr;  // debug hook (gpar_debug_set_dataflow_prof)
 
 static void set_smem_attrs() {
   static bool done = false;
@@ -657,6 +703,7 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
     p.ws = ws; p.strideWs = strideWs;
     p.pool = ws + batch * strideWs;
     p.info = info;
+    p.prof = g_df_prof;
     int* ints = reinterpret_cast<int*>(p.pool + (int64_t)DF_POOL_TILES * TILE * TILE);
     p.ticket = ints; p.ready = ints + 2;
     cudaMemsetAsync(ints, 0, sizeof(int) * (size_t)ws_ready_ints(nt, nbt, batch), stream);
@@ -669,7 +716,7 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
     const int64_t j0 = (int64_t)k * TILE;
     const int kb = (int)((n - j0 < TILE) ? (n - j0) : TILE);
     potrf_diag_kernel<<<(unsigned)batch, 256, DIAG_SMEM_BYTES, stream>>>(A, lda, strideA, k, nt, n, ws, strideWs,
-                                                                       info);
+                                                                       info, nullptr);
     const int64_t below = n - (j0 + TILE);
     const double* Linv = ws + (int64_t)k * TILE * TILE;
     const int ntr = below > 0 ? (int)((below + TILE - 1) / TILE) : 0;
@@ -727,4 +774,19 @@ extern "C" int gpar_syrk_sub(double* C, int64_t ldc, int64_t n, int64_t strideC,
   p.C2 = nullptr; p.ldc2 = 0; p.c_rows2 = 0; p.strideC2 = 0; p.Aop2 = nullptr; p.lda2 = 0; p.strideA2 = 0;
   gemm_sub_kernel<<<dim3(nt, nt, (unsigned)batch), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
   return check_launch("gpar_syrk_sub");
+}
+
+// Debug: phase timestamps (clock64) of the diagonal-tile factor on the leading 128 block of A.
+extern "C" int gpar_debug_diag_profile(double* A, int64_t lda, int64_t n, double* ws, int32_t* info, long long* prof,
+                                       void* stream_) {
+  set_smem_attrs();
+  const int nt = (int)((n + TILE - 1) / TILE);
+  potrf_diag_kernel<<<1, 256, DIAG_SMEM_BYTES, (cudaStream_t)stream_>>>(A, lda, 0, 0, nt, n, ws, ws_stride(nt, 0), info,
+                                                                        prof);
+  return check_launch("gpar_debug_diag_profile");
+}
+
+extern "C" int gpar_debug_set_dataflow_prof(long long* prof) {
+  gpar::g_df_prof = prof;
+  return 0;
 }

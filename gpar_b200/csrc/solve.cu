@@ -5,39 +5,76 @@
 
 namespace gpar {
 
-// ---- backward solve, one 128-block step -------------------------------------------------
-// work holds the running right-hand side.  Step bt: alpha_b = Linv_bb^T work_b (every CTA
-// recomputes it: 16K MACs), CTA c == bt publishes alpha_b, CTA c < bt applies
-// work_c -= L[b, c]^T alpha_b.
-__global__ void __launch_bounds__(128)
-backsolve_step_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const double* __restrict__ ws,
-                      double* __restrict__ work, double* __restrict__ alpha, int bt) {
-  __shared__ double ub[TILE];
-  __shared__ double ab[TILE];
-  const int c = blockIdx.x, t = threadIdx.x;
-  const int64_t r0 = (int64_t)bt * TILE;
-  const int kb = static_cast<int>(min64(TILE, n - r0));
-  ub[t] = (t < kb) ? work[r0 + t] : 0.0;
-  __syncthreads();
-  const double* Linv = ws + (int64_t)bt * TILE * TILE;
-  double s = 0.0;
-  for (int r = t; r < kb; ++r) s = fma(Linv[r * TILE + t], ub[r], s);
-  ab[t] = s;
-  __syncthreads();
-  if (c == bt) {
-    if (t < kb) alpha[r0 + t] = s;
-    return;
+// ---- backward solve alpha = L^-T u in ONE launch -------------------------------------------
+// CTA c owns the 128-block b = nt-1-c of alpha (block index descending with blockIdx, so every
+// dependency points at a CTA that was scheduled earlier: no co-residency requirement).  It
+// accumulates s = sum_{k>b} L[k, b]^T alpha_k tile by tile as the alpha_k are published
+// (acquire/release flags), then alpha_b = Linv_bb^T (u_b - s).  Loads are 16-way unrolled
+// (memory-level parallelism); the chain per block is one tile GEMV + one 128x128 matvec.
+__device__ __forceinline__ int ld_acquire_i(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// partial[c] = sum_{r in this thread's row half} M[r * ldm + c] * v[r]  for column c = tid & 127
+__device__ __forceinline__ double tile_col_dot(const double* __restrict__ M, int64_t ldm, const double* v_s,
+                                               int r_begin, int r_end) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  int r = r_begin;
+  for (; r + 16 <= r_end; r += 16) {
+    double x[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) x[q] = __ldcg(M + (int64_t)(r + q) * ldm);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q & 3] = fma(x[q], v_s[r + q], acc[q & 3]);
   }
-  const int64_t c0 = (int64_t)c * TILE;
-  const double* Lb = L + r0 * ldl + c0 + t;
-  double acc0 = 0.0, acc1 = 0.0;
-  int r = 0;
-  for (; r + 1 < kb; r += 2) {
-    acc0 = fma(Lb[(int64_t)r * ldl], ab[r], acc0);
-    acc1 = fma(Lb[(int64_t)(r + 1) * ldl], ab[r + 1], acc1);
+  for (; r < r_end; ++r) acc[0] = fma(__ldcg(M + (int64_t)r * ldm), v_s[r], acc[0]);
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+__global__ void __launch_bounds__(256)
+backsolve_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const double* __restrict__ ws,
+                 const double* __restrict__ u, double* __restrict__ alpha, int* __restrict__ ready, int nt) {
+  __shared__ double v_s[TILE];
+  __shared__ double part[2][TILE];
+  const int b = nt - 1 - blockIdx.x;
+  const int t = threadIdx.x, c = t & 127, h = t >> 7;
+  const int64_t c0 = (int64_t)b * TILE;
+  const int kb = static_cast<int>(min64(TILE, n - c0));
+  double s = 0.0;  // threads t < 128 hold the running sum for column c0 + t
+  for (int k = nt - 1; k > b; --k) {
+    const int64_t r0 = (int64_t)k * TILE;
+    const int kr = static_cast<int>(min64(TILE, n - r0));
+    while (ld_acquire_i(ready + k) == 0) __nanosleep(20);
+    __syncthreads();
+    if (t < TILE) v_s[t] = (t < kr) ? __ldcg(alpha + r0 + t) : 0.0;
+    __syncthreads();
+    const int half = (kr + 1) / 2;
+    double pv = 0.0;
+    if (c < kb) pv = tile_col_dot(L + r0 * ldl + c0 + c, ldl, v_s, h ? half : 0, h ? kr : half);
+    part[h][c] = pv;
+    __syncthreads();
+    if (t < TILE) s += part[0][t] + part[1][t];
   }
-  if (r < kb) acc0 = fma(Lb[(int64_t)r * ldl], ab[r], acc0);
-  work[c0 + t] -= (acc0 + acc1);
+  __syncthreads();
+  if (t < TILE) v_s[t] = (t < kb) ? u[c0 + t] - s : 0.0;
+  __syncthreads();
+  // alpha_b[i] = sum_{r >= i} Linv[r][i] v[r]
+  const double* Linv = ws + (int64_t)b * TILE * TILE;
+  const int half = (kb + 1) / 2;
+  double pv = 0.0;
+  // column c of Linv is stored from the top of its 8x8 diagonal block downwards
+  if (c < kb) {
+    const int lo = c & ~7, mid = lo + (kb - lo + 1) / 2;
+    pv = tile_col_dot(Linv + c, TILE, v_s, h ? mid : lo, h ? kb : mid);
+  }
+  part[h][c] = pv;
+  __syncthreads();
+  if (t < kb) alpha[c0 + t] = part[0][t] + part[1][t];
+  __threadfence();
+  __syncthreads();
+  if (t == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(ready + b), "r"(1) : "memory");
 }
 
 __global__ void __launch_bounds__(1024)
@@ -191,9 +228,71 @@ __global__ void __launch_bounds__(256) probe_dfma_kernel(int64_t iters, double* 
   if (s == 123.456) sink[0] = s;
 }
 
+// Single-warp dependent-chain latency probes (cycles per op), for designing the Cholesky critical path.
+__global__ void probe_latency_kernel(double* out, double seed) {
+  __shared__ double sm[64];
+  const int lane = threadIdx.x;
+  sm[lane] = seed + lane; sm[lane + 32] = 1.0;
+  __syncthreads();
+  const int N = 256;
+  long long t0, t1;
+  double r[10];
+  // 0: dependent DMMA chain (one accumulator)
+  { double c0 = 0, c1 = 0, a = seed, b = 1.0; t0 = clock64();
+    for (int i = 0; i < N; ++i) dmma884(c0, c1, a, b);
+    t1 = clock64(); r[0] = (double)(t1 - t0) / N; sm[0] += c0 + c1; }
+  // 1: 4 accumulators round-robin (k-step structure of strip_mma): per k-step
+  { double c[4][2] = {{0,0},{0,0},{0,0},{0,0}}; double a = seed, b = 1.0; t0 = clock64();
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) dmma884(c[t][0], c[t][1], a, b); }
+    t1 = clock64(); r[1] = (double)(t1 - t0) / N; sm[1] += c[0][0] + c[1][0] + c[2][1] + c[3][1]; }
+  // 2: dependent DFMA chain
+  { double x = seed; t0 = clock64();
+    for (int i = 0; i < N; ++i) x = fma(x, 1.0000001, 1e-9);
+    t1 = clock64(); r[2] = (double)(t1 - t0) / N; sm[2] += x; }
+  // 3: double shuffle chain
+  { double x = seed + lane; t0 = clock64();
+    for (int i = 0; i < N; ++i) x = __shfl_sync(0xffffffffu, x, (lane + 1) & 31);
+    t1 = clock64(); r[3] = (double)(t1 - t0) / N; sm[3] += x; }
+  // 4: rsqrt chain
+  { double x = seed + 2.0; t0 = clock64();
+    for (int i = 0; i < N; ++i) x = rsqrt(x) + 1.5;
+    t1 = clock64(); r[4] = (double)(t1 - t0) / N; sm[4] += x; }
+  // 5: sqrt chain
+  { double x = seed + 2.0; t0 = clock64();
+    for (int i = 0; i < N; ++i) x = sqrt(x) + 1.5;
+    t1 = clock64(); r[5] = (double)(t1 - t0) / N; sm[5] += x; }
+  // 6: division chain
+  { double x = seed + 2.0; t0 = clock64();
+    for (int i = 0; i < N; ++i) x = 3.0 / x + 1.5;
+    t1 = clock64(); r[6] = (double)(t1 - t0) / N; sm[6] += x; }
+  // 7: shared-memory store -> syncwarp -> load round trip chain
+  { double x = seed; t0 = clock64();
+    for (int i = 0; i < N; ++i) { sm[32 + lane] = x; __syncwarp(); x = sm[32 + ((lane + 1) & 31)] + 1.0; __syncwarp(); }
+    t1 = clock64(); r[7] = (double)(t1 - t0) / N; sm[7] += x; }
+  // 8: fast reciprocal-sqrt seed (MUFU.RSQ64H) + one Newton step
+  { double x = seed + 2.0; t0 = clock64();
+    for (int i = 0; i < N; ++i) {
+      double y = __longlong_as_double(((long long)__double2hiint(x)) << 32);  // placeholder dependency
+      float xf = (float)x; float yf = rsqrtf(xf); y = (double)yf;
+      double e = fma(-x * y, y, 1.0); y = fma(y * e, fma(e, 0.375, 0.5), y);
+      e = fma(-x * y, y, 1.0); y = fma(y * e, fma(e, 0.375, 0.5), y);
+      x = y + 1.5; }
+    t1 = clock64(); r[8] = (double)(t1 - t0) / N; sm[8] += x; }
+  if (lane == 0) for (int i = 0; i < 9; ++i) out[i] = r[i];
+  if (sm[lane & 7] == 12345.678) out[20] = sm[lane];
+}
+
 }  // namespace gpar
 
 using namespace gpar;
+
+extern "C" int gpar_debug_latency_probe(double* out, void* stream) {
+  probe_latency_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(out, 1.25);
+  return check_launch("gpar_debug_latency_probe");
+}
+
 
 extern "C" int gpar_backsolve(const double* L, int64_t ldl, int64_t n, const double* ws, const double* u,
                               double* alpha, double* work, void* stream_) {
@@ -202,10 +301,10 @@ extern "C" int gpar_backsolve(const double* L, int64_t ldl, int64_t n, const dou
   if (!ws) return -4;
   if (!u || !alpha || !work) { set_error("gpar_backsolve: null vector"); return -5; }
   if (n <= 0) return 0;
-  cudaMemcpyAsync(work, u, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream);
   const int nt = (int)((n + TILE - 1) / TILE);
-  for (int bt = nt - 1; bt >= 0; --bt)
-    backsolve_step_kernel<<<bt + 1, 128, 0, stream>>>(L, ldl, n, ws, work, alpha, bt);
+  // `work` (n doubles) hosts the nt ready flags.
+  cudaMemsetAsync(work, 0, sizeof(int) * (size_t)nt, stream);
+  backsolve_kernel<<<nt, 256, 0, stream>>>(L, ldl, n, ws, u, alpha, reinterpret_cast<int*>(work), nt);
   return check_launch("gpar_backsolve");
 }
 

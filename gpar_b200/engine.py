@@ -124,7 +124,7 @@ class Engine:
         rc = self.lib.gpar_backsolve(self.addr(L), ldl, n, self.addr(ws), self.addr(u), self.addr(alpha),
                                      self.addr(work), self.stream)
         check(rc, "gpar_backsolve")
-        self.launches += (n + TILE - 1) // TILE
+        self.launches += 1
         return alpha
 
     def logdet_quad(self, L, ldl, n, u, out2, l_off=0, u_off=0, out_off=0):

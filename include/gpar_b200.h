@@ -152,6 +152,15 @@ int gpar_mean_axis0(const double* in, int64_t ns, int64_t n, double* out, void* 
  * number of flops executed per launch through *flops. */
 int gpar_fp64_probe(int mode, int64_t iters, double* sink, double* flops, void* stream);
 
+/* Debug: single-warp dependent-chain latencies in cycles (out: >= 32 doubles). */
+int gpar_debug_latency_probe(double* out, void* stream);
+/* Debug: when non-null, gpar_potrf records globaltimer stamps (24 values) of the tile tasks
+ * around column nt/2 of matrix 0 into prof. */
+int gpar_debug_set_dataflow_prof(long long* prof);
+/* Debug: clock64 phase timestamps (21 values) of the diagonal-tile factor on A[0:128, 0:128]. */
+int gpar_debug_diag_profile(double* A, int64_t lda, int64_t n, double* ws, int32_t* info, long long* prof,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,26 @@
+import os, sys, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from gpar_b200.engine import Engine
+from gpar_b200.spec import lower_terms
+eng = Engine()
+spec = lower_terms([dict(type="eq", variance=1.0, cols=[0, 1, 2, 3], scales=[0.25] * 4)])
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 7424
+X = torch.rand(n, 4, dtype=torch.float64, device=eng.device).reshape(-1)
+d = torch.full((n,), 0.1, dtype=torch.float64, device=eng.device)
+J = eng.empty(n * n); u = eng.zeros(n)
+prof = torch.zeros(32, dtype=torch.int64, device=eng.device)
+eng.lib.gpar_debug_set_dataflow_prof(C.c_void_p(prof.data_ptr()))
+for _ in range(2):
+    eng.gram(spec, X, 4, n, J, n, diag=d, lower_only=True)
+    eng.potrf(J, n, n, B=u, ldb=n, nb=1)
+    torch.cuda.synchronize()
+eng.lib.gpar_debug_set_dataflow_prof(None)
+p = prof.cpu().numpy().astype(np.int64)
+t0 = p[0]
+lab = ["task start", "K-loop done", "C stored+fenced", "diag flag seen", "solve/factor done", "flag published"]
+for base, name in ((0, "diag (jp,jp)"), (8, "offdiag (jp+1,jp)"), (16, "diag (jp+1,jp+1)")):
+    print(name)
+    for i in range(6):
+        if p[base + i]: print(f"   {lab[i]:20s} t = {(p[base+i]-t0)/1e3:9.2f} us")
+print("diag-to-diag period:", (p[16 + 5] - p[5]) / 1e3, "us")
