@@ -17,61 +17,68 @@ __device__ __forceinline__ int ld_acquire_i(const int* p) {
   return v;
 }
 
-// partial[c] = sum_{r in this thread's row half} M[r * ldm + c] * v[r]  for column c = tid & 127
-__device__ __forceinline__ double tile_col_dot(const double* __restrict__ M, int64_t ldm, const double* v_s,
-                                               int r_begin, int r_end) {
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  int r = r_begin;
-  for (; r + 16 <= r_end; r += 16) {
-    double x[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) x[q] = __ldcg(M + (int64_t)(r + q) * ldm);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) acc[q & 3] = fma(x[q], v_s[r + q], acc[q & 3]);
-  }
-  for (; r < r_end; ++r) acc[0] = fma(__ldcg(M + (int64_t)r * ldm), v_s[r], acc[0]);
-  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
-}
-
-__global__ void __launch_bounds__(256)
+// 512 threads: column c = t & 127 of the block, row quarter q = t >> 7 (32 rows each).  The 32
+// tile values a thread needs for step k are loaded BEFORE it waits for alpha_k (they only depend
+// on the factor), so the dependent chain per block is flag -> 32 FMAs -> shared reduce -> 32 FMAs.
+__global__ void __launch_bounds__(512)
 backsolve_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const double* __restrict__ ws,
                  const double* __restrict__ u, double* __restrict__ alpha, int* __restrict__ ready, int nt) {
   __shared__ double v_s[TILE];
-  __shared__ double part[2][TILE];
+  __shared__ double part[4][TILE];
   const int b = nt - 1 - blockIdx.x;
-  const int t = threadIdx.x, c = t & 127, h = t >> 7;
+  const int t = threadIdx.x, c = t & 127, q = t >> 7;
   const int64_t c0 = (int64_t)b * TILE;
   const int kb = static_cast<int>(min64(TILE, n - c0));
-  double s = 0.0;  // threads t < 128 hold the running sum for column c0 + t
+  const bool col_ok = c < kb;
+  // this thread's quarter of column c of Linv_bb (rows 32 q .. 32 q + 31), kept in registers
+  const double* Linv = ws + (int64_t)b * TILE * TILE;
+  double li[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int r = 32 * q + i;
+    li[i] = (col_ok && r < kb && r >= (c & ~7)) ? __ldcg(Linv + r * TILE + c) : 0.0;
+  }
+  double s = 0.0;  // threads with q == 0 hold the running sum for column c0 + c
   for (int k = nt - 1; k > b; --k) {
     const int64_t r0 = (int64_t)k * TILE;
     const int kr = static_cast<int>(min64(TILE, n - r0));
+    double x[32];
+    const double* Lt = L + (r0 + 32 * q) * ldl + c0 + c;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = (col_ok && 32 * q + i < kr) ? __ldcg(Lt + (int64_t)i * ldl) : 0.0;
     while (ld_acquire_i(ready + k) == 0) __nanosleep(20);
-    __syncthreads();
+    __syncthreads();  // previous step's readers of v_s / part are done
     if (t < TILE) v_s[t] = (t < kr) ? __ldcg(alpha + r0 + t) : 0.0;
     __syncthreads();
-    const int half = (kr + 1) / 2;
-    double pv = 0.0;
-    if (c < kb) pv = tile_col_dot(L + r0 * ldl + c0 + c, ldl, v_s, h ? half : 0, h ? kr : half);
-    part[h][c] = pv;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      a0 = fma(x[i], v_s[32 * q + i], a0);
+      a1 = fma(x[i + 1], v_s[32 * q + i + 1], a1);
+      a2 = fma(x[i + 2], v_s[32 * q + i + 2], a2);
+      a3 = fma(x[i + 3], v_s[32 * q + i + 3], a3);
+    }
+    part[q][c] = (a0 + a1) + (a2 + a3);
     __syncthreads();
-    if (t < TILE) s += part[0][t] + part[1][t];
+    if (q == 0) s += (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
   }
   __syncthreads();
-  if (t < TILE) v_s[t] = (t < kb) ? u[c0 + t] - s : 0.0;
+  if (q == 0) v_s[c] = col_ok ? u[c0 + c] - s : 0.0;
   __syncthreads();
-  // alpha_b[i] = sum_{r >= i} Linv[r][i] v[r]
-  const double* Linv = ws + (int64_t)b * TILE * TILE;
-  const int half = (kb + 1) / 2;
-  double pv = 0.0;
-  // column c of Linv is stored from the top of its 8x8 diagonal block downwards
-  if (c < kb) {
-    const int lo = c & ~7, mid = lo + (kb - lo + 1) / 2;
-    pv = tile_col_dot(Linv + c, TILE, v_s, h ? mid : lo, h ? kb : mid);
+  // alpha_b[c] = sum_r Linv[r][c] v[r]
+  {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      a0 = fma(li[i], v_s[32 * q + i], a0);
+      a1 = fma(li[i + 1], v_s[32 * q + i + 1], a1);
+      a2 = fma(li[i + 2], v_s[32 * q + i + 2], a2);
+      a3 = fma(li[i + 3], v_s[32 * q + i + 3], a3);
+    }
+    part[q][c] = (a0 + a1) + (a2 + a3);
   }
-  part[h][c] = pv;
   __syncthreads();
-  if (t < kb) alpha[c0 + t] = part[0][t] + part[1][t];
+  if (q == 0 && col_ok) alpha[c0 + c] = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
   __threadfence();
   __syncthreads();
   if (t == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(ready + b), "r"(1) : "memory");
@@ -304,7 +311,7 @@ extern "C" int gpar_backsolve(const double* L, int64_t ldl, int64_t n, const dou
   const int nt = (int)((n + TILE - 1) / TILE);
   // `work` (n doubles) hosts the nt ready flags.
   cudaMemsetAsync(work, 0, sizeof(int) * (size_t)nt, stream);
-  backsolve_kernel<<<nt, 256, 0, stream>>>(L, ldl, n, ws, u, alpha, reinterpret_cast<int*>(work), nt);
+  backsolve_kernel<<<nt, 512, 0, stream>>>(L, ldl, n, ws, u, alpha, reinterpret_cast<int*>(work), nt);
   return check_launch("gpar_backsolve");
 }
 
