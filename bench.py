@@ -370,23 +370,41 @@ def measure_fp64_peaks(eng):
 
 
 def measure_dominant_kernel(eng, peaks):
-    """Roofline of the dominant kernel (gemm_sub_kernel: the trailing SYRK update of the blocked
-    Cholesky, fp64 DMMA).  One launch = C(n x n, lower) -= W W^T with W n x 128 at the size of the
-    first trailing update of a C3 layer; algorithmic flops = n (n + 1) * 128."""
+    """Roofline of the dominant kernel, potrf_dataflow_kernel (persistent tile-dataflow Cholesky,
+    fp64 DMMA): one launch factors the joint [training; test] matrix of a C3 layer (n = 8424 rows,
+    one appended right-hand-side row).  Algorithmic flops per launch = n^3 / 3 + n^2 (SURVEY 8(d));
+    duration = CUDA events around the launch on the launching stream (mean of 5, after warm-up)."""
     import torch
 
-    n, k = 8192, 128
+    from gpar_b200.spec import lower_terms
+
+    n = 8424
     ld = n
-    Cm = torch.zeros(n * ld, dtype=torch.float64, device=eng.device)
-    Wm = torch.randn(n * k, dtype=torch.float64, device=eng.device)
-    best, avg = _time_events(lambda: eng.syrk_sub(Cm, ld, n, Wm, k, k), 10)
-    flops = float(n) * (n + 1) * k
+    spec = lower_terms([dict(type="eq", variance=1.0, cols=[0, 1, 2, 3], scales=[0.25] * 4)])
+    X = torch.rand(n * 4, dtype=torch.float64, device=eng.device)
+    d = torch.full((n,), 0.1, dtype=torch.float64, device=eng.device)
+    J = eng.empty(n * ld)
+    u = eng.zeros(ld)
+    times = []
+    for it in range(7):
+        eng.gram(spec, X, 4, n, J, ld, diag=d, lower_only=True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.potrf(J, ld, n, B=u, ldb=ld, nb=1)
+        b.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            times.append(a.elapsed_time(b) / 1e3)
+    avg = float(np.mean(times))
+    flops = n ** 3 / 3.0 + float(n) ** 2
     ach = flops / avg / 1e12
-    return {"kernel": "gemm_sub_kernel (trailing SYRK update, DMMA m8n8k4)", "bound": "tensor",
+    # HBM side of the same launch: the lower triangle is read once and written once (left-looking)
+    alg_bytes = 2 * 8.0 * n * (n + 1) / 2
+    return {"kernel": "potrf_dataflow_kernel (persistent tile-dataflow Cholesky, DMMA m8n8k4)", "bound": "tensor",
             "achieved": ach, "peak": peaks["dgemm_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["dgemm_tflops"],
-            "traffic": None, "launch_ms": avg * 1e3,
+            "traffic": None, "launch_ms": avg * 1e3, "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes,
             "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (MEASURED_PEAKS.json has no fp64 entry)",
-            "shape": {"n": n, "k": k}}
+            "shape": {"n": n, "appended_rows": 1}}
 
 
 if __name__ == "__main__":
