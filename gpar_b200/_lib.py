@@ -62,6 +62,9 @@ SIGNATURES = {
     "gpar_potrf": (_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "gpar_trsm_rows": (_int, [_p, _i64, _i64, _p, _p, _i64, _i64, _p, _p]),
     "gpar_syrk_sub": (_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p]),
+    "gpar_syrk_add": (_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p]),
+    "gpar_transpose_scale": (_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
+    "gpar_vfe_rowterms": (_int, [_SPEC, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p]),
     "gpar_backsolve": (_int, [_p, _i64, _i64, _p, _p, _p, _p, _p]),
     "gpar_logdet_quad": (_int, [_p, _i64, _i64, _p, _p, _p]),
     "gpar_gemv": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),

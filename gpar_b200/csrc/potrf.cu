@@ -388,7 +388,7 @@ struct SubArgs {
   double* C; int64_t ldc; int64_t c_rows; int64_t c_cols; int64_t strideC;
   const double* Aop; int64_t lda; int64_t strideA;
   const double* Bop; int64_t ldb; int64_t strideB;
-  int K; int lower; int nt_rows1;
+  int K; int lower; int nt_rows1; int add;  // add != 0: C += A B^T instead of C -= A B^T
   // secondary row space (appended rows, row tiles >= nt_rows1): all column tiles
   double* C2; int64_t ldc2; int64_t c_rows2; int64_t strideC2;
   const double* Aop2; int64_t lda2; int64_t strideA2;
@@ -424,6 +424,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_sub_kernel(const SubArgs
   Acc acc;
   acc_zero(acc);
   gemm_nt_mainloop<0>(stages, Ap, lda, rows, Bp, p.ldb, cols, p.K, acc);
+  if (p.add) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[i][j][0] = -acc[i][j][0];
+        acc[i][j][1] = -acc[i][j][1];
+      }
+  }
   store_tile<1>(C, ldc, rows, cols, acc, lower_diag);
 }
 
@@ -732,7 +741,7 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
       p.C = A + (j0 + TILE) * lda + (j0 + TILE); p.ldc = lda; p.c_rows = below; p.c_cols = below; p.strideC = strideA;
       p.Aop = A + (j0 + TILE) * lda + j0; p.lda = lda; p.strideA = strideA;
       p.Bop = p.Aop; p.ldb = lda; p.strideB = strideA;
-      p.K = kb; p.lower = 1; p.nt_rows1 = ntr;
+      p.K = kb; p.lower = 1; p.nt_rows1 = ntr; p.add = 0;
       p.C2 = nb > 0 ? B + (j0 + TILE) : nullptr; p.ldc2 = ldb; p.c_rows2 = nb; p.strideC2 = strideB;
       p.Aop2 = nb > 0 ? B + j0 : nullptr; p.lda2 = ldb; p.strideA2 = strideB;
       gemm_sub_kernel<<<dim3((unsigned)ntr, (unsigned)(ntr + nbt), (unsigned)batch), GEMM_THREADS, GEMM_SMEM_BYTES,
@@ -756,8 +765,21 @@ extern "C" int gpar_trsm_rows(const double* L, int64_t ldl, int64_t n, const dou
   return check_launch("gpar_trsm_rows");
 }
 
+static int syrk_impl(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw, int64_t k,
+                     int64_t strideW, int64_t batch, int add, void* stream_);
+
 extern "C" int gpar_syrk_sub(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw,
                              int64_t k, int64_t strideW, int64_t batch, void* stream_) {
+  return syrk_impl(C, ldc, n, strideC, W, ldw, k, strideW, batch, 0, stream_);
+}
+
+extern "C" int gpar_syrk_add(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw,
+                             int64_t k, int64_t strideW, int64_t batch, void* stream_) {
+  return syrk_impl(C, ldc, n, strideC, W, ldw, k, strideW, batch, 1, stream_);
+}
+
+static int syrk_impl(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw, int64_t k,
+                     int64_t strideW, int64_t batch, int add, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!C || !aligned16(C) || (ldc & 1) || ldc < n) { set_error("gpar_syrk_sub: bad C"); return -1; }
   if (!W || !aligned16(W) || (ldw & 1) || ldw < k) { set_error("gpar_syrk_sub: bad W"); return -5; }
@@ -770,7 +792,7 @@ extern "C" int gpar_syrk_sub(double* C, int64_t ldc, int64_t n, int64_t strideC,
   p.C = C; p.ldc = ldc; p.c_rows = n; p.c_cols = n; p.strideC = strideC;
   p.Aop = W; p.lda = ldw; p.strideA = strideW;
   p.Bop = W; p.ldb = ldw; p.strideB = strideW;
-  p.K = (int)k; p.lower = 1; p.nt_rows1 = (int)nt;
+  p.K = (int)k; p.lower = 1; p.nt_rows1 = (int)nt; p.add = add;
   p.C2 = nullptr; p.ldc2 = 0; p.c_rows2 = 0; p.strideC2 = 0; p.Aop2 = nullptr; p.lda2 = 0; p.strideA2 = 0;
   gemm_sub_kernel<<<dim3(nt, nt, (unsigned)batch), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
   return check_launch("gpar_syrk_sub");

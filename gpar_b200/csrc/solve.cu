@@ -204,6 +204,66 @@ __global__ void mean_axis0_kernel(const double* __restrict__ in, int64_t ns, int
   out[i] = s / (double)ns;
 }
 
+// ---- VFE helpers -------------------------------------------------------------
+// dst (cols x rows, ldd) = transpose(src (rows x cols, lds)) with row r of src scaled by scale[r].
+__global__ void __launch_bounds__(256)
+transpose_scale_kernel(const double* __restrict__ src, int64_t lds, int64_t rows, int64_t cols,
+                       const double* __restrict__ scale, double* __restrict__ dst, int64_t ldd) {
+  __shared__ double tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    double v = 0.0;
+    if (r < rows && c < cols) v = src[r * lds + c] * (scale ? scale[r] : 1.0);
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) dst[c * ldd + r] = tile[tx][i];
+  }
+}
+
+// out[0] = sum_j [ (k(x_j, x_j) - ||Bt_j||^2) / sigma_j + log(2 pi sigma_j) + y_j^2 / sigma_j ]
+// (trace, normaliser and data terms of the Titsias bound; Bt = K_xz L_z^-T is n x M).  One CTA:
+// deterministic reduction.
+__global__ void __launch_bounds__(1024)
+vfe_rowterms_kernel(const __grid_constant__ gpar_kernel_spec_t spec, const double* __restrict__ X, int64_t ldx,
+                    int64_t n, const double* __restrict__ Bt, int64_t ldb, int64_t M,
+                    const double* __restrict__ sigma, const double* __restrict__ y, double* __restrict__ out) {
+  __shared__ double red[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  double acc = 0.0;
+  for (int64_t j = warp; j < n; j += nw) {
+    const double* b = Bt + j * ldb;
+    double ss = 0.0;
+    for (int64_t c = lane; c < M; c += 32) ss = fma(b[c], b[c], ss);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      double kjj = 0.0;
+      const double* xr = X + j * ldx;
+      for (int t = 0; t < spec.n_terms; ++t) {
+        const gpar_term_t& T = spec.terms[t];
+        if (T.type == GPAR_TERM_LINEAR) {
+          double a = 0.0;
+          for (int f = T.f_begin; f < T.f_end; ++f) {
+            const double ph = eval_feature(spec, f, xr);
+            a = fma(ph, ph, a);
+          }
+          kjj = fma(T.variance, a, kjj);
+        } else {
+          kjj += T.variance;  // EQ / RQ / const at zero distance
+        }
+      }
+      const double sg = sigma[j], yy = y[j];
+      acc += (kjj - ss) / sg + log(6.283185307179586 * sg) + yy * yy / sg;
+    }
+  }
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) out[0] = tot;
+}
+
 // ---- fp64 issue-rate probes -------------------------------------------------------------
 __global__ void __launch_bounds__(256) probe_dmma_kernel(int64_t iters, double* sink) {
   double c[16][2];
@@ -368,6 +428,24 @@ extern "C" int gpar_mean_axis0(const double* in, int64_t ns, int64_t n, double* 
   if (n <= 0 || ns <= 0) return 0;
   mean_axis0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, ns, n, out);
   return check_launch("gpar_mean_axis0");
+}
+
+extern "C" int gpar_transpose_scale(const double* src, int64_t lds, int64_t rows, int64_t cols, const double* scale,
+                                    double* dst, int64_t ldd, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!src || !dst) return -1;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  if (grid.y > 65535) { set_error("gpar_transpose_scale: too many rows"); return -3; }
+  transpose_scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, rows, cols, scale, dst, ldd);
+  return check_launch("gpar_transpose_scale");
+}
+
+extern "C" int gpar_vfe_rowterms(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t n,
+                                 const double* Bt, int64_t ldb, int64_t M, const double* sigma, const double* y,
+                                 double* out, void* stream) {
+  if (!spec || !out) return -1;
+  vfe_rowterms_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*spec, X, ldx, n, Bt, ldb, M, sigma, y, out);
+  return check_launch("gpar_vfe_rowterms");
 }
 
 extern "C" int gpar_fp64_probe(int mode, int64_t iters, double* sink, double* flops, void* stream) {

@@ -117,6 +117,25 @@ class Engine:
         self.launches += 1
         self.flops += batch * float(n) ** 2 * k
 
+    def syrk_add(self, Cm, ldc, n, W, ldw, k, batch=1, strideC=0, strideW=0):
+        rc = self.lib.gpar_syrk_add(self.addr(Cm), ldc, n, strideC, self.addr(W), ldw, k, strideW, batch, self.stream)
+        check(rc, "gpar_syrk_add")
+        self.launches += 1
+        self.flops += batch * float(n) ** 2 * k
+
+    # -- K8 -------------------------------------------------------------------
+    def transpose_scale(self, src, lds, rows, cols, scale, dst, ldd):
+        rc = self.lib.gpar_transpose_scale(self.addr(src), lds, rows, cols, None if scale is None else self.addr(scale),
+                                           self.addr(dst), ldd, self.stream)
+        check(rc, "gpar_transpose_scale")
+        self.launches += 1
+
+    def vfe_rowterms(self, spec, X, ldx, n, Bt, ldb, M, sigma, y, out, out_off=0):
+        rc = self.lib.gpar_vfe_rowterms(C.byref(spec), self.addr(X), ldx, n, self.addr(Bt), ldb, M, self.addr(sigma),
+                                        self.addr(y), self.addr(out, out_off), self.stream)
+        check(rc, "gpar_vfe_rowterms")
+        self.launches += 1
+
     # -- K3 -------------------------------------------------------------------
     def backsolve(self, L, ldl, n, ws, u):
         alpha = self.empty(max(n, 1))

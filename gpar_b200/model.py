@@ -338,6 +338,8 @@ class GPAR:
         if self.sparse:
             from .sparse import logpdf_sparse
 
+            if sample_missing:
+                raise NotImplementedError("sample_missing is not supported with inducing points")
             return logpdf_sparse(self, x, y, w, only_last_layer, return_inputs, x_ind, outputs)
         eng = self.engine
         if not isinstance(y, dict):

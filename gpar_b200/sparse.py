@@ -1,0 +1,280 @@
+"""Inducing-point (VFE / Titsias) path of GPAR -- the counterpart of stheno's ``PseudoObs``
+as driven by gpar/model.py:286-287, 303-305.
+
+Per layer, with inducing inputs z (M x d), observed rows x (n x d), noise diagonal sigma = noise / w
+and targets y (prior mean zero):
+
+    L_z  = chol(K_zz + eps I)                      B^T = K_xz L_z^-T          (one gpar_potrf call: K_xz
+                                                                              rides along as appended rows)
+    A    = I + B Sigma^-1 B^T                      c   = B Sigma^-1 y
+    ELBO = -1/2 [ sum_j (k_jj - |b_j|^2)/sigma_j + sum_j log(2 pi sigma_j) + logdet A
+                  + sum_j y_j^2/sigma_j - c^T A^-1 c ]
+    mean(x_)      = K(x_, z) beta,   beta = L_z^-T A^-1 c
+    cov(x_, x_')  = k - B_x^T B_x' + (L_A^-1 B_x)^T (L_A^-1 B_x')
+
+Every step is one of the engine's kernels; the host only prepares sigma-derived vectors.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .engine import Factor, F64, _even
+from .model import DevMat, ObsBlock, _stack, construct_model, last, per_output
+from .spec import LayerModel
+
+__all__ = ["SparseFactor", "logpdf_sparse", "condition_sparse", "sample_sparse"]
+
+
+class SparseBlock:
+    """Observations of a sparse posterior layer: inducing inputs, observed rows, targets, noise."""
+
+    def __init__(self, Z, X, y_host, sig_host):
+        self.Z, self.X, self.y_host, self.sig_host = Z, X, y_host, sig_host
+        self.n = X.n
+        self.factor = None
+
+
+class SparseFactor:
+    def __init__(self, eng, spec, Z, X, y_host, sig_host):
+        self.eng, self.spec, self.Z, self.X = eng, spec, Z, X
+        M, n = Z.n, X.n
+        self.M, self.n = M, n
+        ldz = self.ldz = _even(max(M, 2))
+        sig = eng.to_device(sig_host)
+        yv = eng.to_device(y_host)
+        # L_z and B^T = K_xz L_z^-T in one sweep
+        self.Jz = eng.empty(M * ldz)
+        eng.gram(spec, Z.t, Z.ld, M, self.Jz, ldz, lower_only=True)  # + eps I on the diagonal
+        self.Bt = eng.empty(max(n, 1) * ldz)
+        if n:
+            eng.gram(spec, X.t, X.ld, n, self.Bt, ldz, Y=Z.t, ldy=Z.ld, ny=M, lower_only=False)
+        self.ws_z, self.info_z = eng.potrf(self.Jz, ldz, M, B=self.Bt if n else None, ldb=ldz, nb=n)
+        # A = I + C^T C with C = diag(sigma^-1/2) B^T, formed as an NT SYRK on C^T (M x n)
+        ldn = _even(max(n, 2))
+        self.JA = torch.eye(M, ldz, dtype=F64, device=eng.device).reshape(-1).contiguous()
+        self.c = eng.zeros(ldz)
+        self.terms = eng.zeros(4)  # [row terms, logdet A, |v|^2]
+        if n:
+            Ct = eng.empty(M * ldn)
+            eng.transpose_scale(self.Bt, ldz, n, M, eng.to_device(1.0 / np.sqrt(sig_host)), Ct, ldn)
+            eng.syrk_add(self.JA, ldz, M, Ct, ldn, n)
+            eng.gemv(Ct, ldn, M, n, eng.to_device(y_host / np.sqrt(sig_host)), self.c)
+            eng.vfe_rowterms(spec, X.t, X.ld, n, self.Bt, ldz, M, sig, yv, self.terms)
+        # v = L_A^-1 c rides along as an appended row
+        self.ws_A, self.info_A = eng.potrf(self.JA, ldz, M, B=self.c, ldb=ldz, nb=1)
+        eng.logdet_quad(self.JA, ldz, M, self.c, self.terms, out_off=1)
+        t = eng.backsolve(self.JA, ldz, M, self.ws_A, self.c)
+        self.beta = eng.backsolve(self.Jz, ldz, M, self.ws_z, t)
+
+    def elbo_slot(self):
+        """Device triple (row terms, logdet A, |v|^2): ELBO = -1/2 (t0 + t1 - t2)."""
+        return self.terms
+
+    def mean_at(self, Xq, ldq, nq, out):
+        self.eng.gram_gemv(self.spec, Xq, ldq, nq, self.Z.t, self.Z.ld, self.M, self.beta, out)
+
+    def _rows_to_factors(self, Xq, nq):
+        """Bs = K_qz L_z^-T and Ds = Bs L_A^-T for nq query rows."""
+        eng, ldz, M = self.eng, self.ldz, self.M
+        Bs = eng.empty(max(nq, 1) * ldz)
+        eng.gram(self.spec, Xq.t, Xq.ld, nq, Bs, ldz, Y=self.Z.t, ldy=self.Z.ld, ny=M, lower_only=False)
+        eng.trsm_rows(self.Jz, ldz, M, self.ws_z, Bs, ldz, nq)
+        Ds = Bs.clone()
+        eng.trsm_rows(self.JA, ldz, M, self.ws_A, Ds, ldz, nq)
+        return Bs, Ds
+
+    def sample_rows(self, Xs, d_s, Z, S, batch, ns, sd=None, Z2=None):
+        """Joint draws at ``batch`` row sets of ``ns`` rows each (stacked in Xs): returns
+        (f_col, y_col, mean) with ``S`` draws per set (S = 1 when batch > 1)."""
+        eng, ldz, M = self.eng, self.ldz, self.M
+        N = batch * ns
+        ldc = _even(max(ns, 2))
+        Cs = eng.empty(batch * ns * ldc)
+        eng.gram_batched(self.spec, Xs.t, Xs.ld, ns, ns * Xs.ld, Cs, ldc, ns * ldc, batch, diag=d_s, strideD=0)
+        Bs, Ds = self._rows_to_factors(Xs, N)
+        eng.syrk_sub(Cs, ldc, ns, Bs, ldz, M, batch=batch, strideC=ns * ldc, strideW=ns * ldz)
+        eng.syrk_add(Cs, ldc, ns, Ds, ldz, M, batch=batch, strideC=ns * ldc, strideW=ns * ldz)
+        eng.potrf(Cs, ldc, ns, batch=batch, strideA=ns * ldc)
+        mean = eng.empty(max(N, 1))
+        self.mean_at(Xs.t, Xs.ld, N, mean)
+        f_col = eng.empty(max(S * N, 1))
+        eng.sample_affine(Cs, ldc, ns, Z, f_col, S, batch=batch, strideC=ns * ldc, mean=mean)
+        y_col = f_col
+        if sd is not None:
+            y_col = eng.empty(max(S * N, 1))
+            eng.sample_affine(Cs, ldc, ns, Z, y_col, S, batch=batch, strideC=ns * ldc, mean=mean,
+                              sd=sd if batch == 1 else sd.repeat(batch), Z2=Z2)
+        return f_col, y_col, mean
+
+
+def _layer(model):
+    layer = model()
+    return layer if isinstance(layer, LayerModel) else layer[0]
+
+
+def _train_step(gpar, layer, xd, zd, y_i, w_i, is_last, blk=None):
+    """One layer of the training-side chain (model.py:165-174 / 220-240 with PseudoObs): returns the
+    factor and the inputs of the next layer."""
+    eng = gpar.engine
+    avail = ~np.isnan(y_i[:, 0])
+    idx = np.flatnonzero(avail)
+    Xa = xd if len(idx) == xd.n else xd.copy_rows(eng.to_device(idx, torch.int64), len(idx))
+    y_a = y_i[avail, 0]
+    sig = layer.noise / w_i[avail]
+    fac = SparseFactor(eng, layer.spec, zd, Xa, y_a, sig)
+    block = SparseBlock(DevMat(eng, zd.t, zd.n, zd.d, zd.ld), DevMat(eng, Xa.t, Xa.n, Xa.d, Xa.ld), y_a, sig)
+    block.factor = fac
+    if is_last:
+        return fac, block, xd, zd
+    # inducing inputs of the next layer (model.py:304-305)
+    est_z = eng.empty(zd.n)
+    fac.mean_at(zd.t, zd.ld, zd.n, est_z)
+    zd_next = zd.with_col(est_z)
+    # y column of the next layer (model.py:307-320)
+    n_i = xd.n
+    col = eng.to_device(y_i[:, 0])
+    miss = ~avail
+    if gpar.impute and gpar.replace:
+        need = np.ones(n_i, dtype=bool)
+    else:
+        need = np.zeros(n_i, dtype=bool)
+        if gpar.impute:
+            need |= miss
+        if gpar.replace:
+            need |= avail
+    if need.any():
+        ridx = eng.to_device(np.flatnonzero(need), torch.int64)
+        Xq = xd if need.all() else xd.copy_rows(ridx, int(need.sum()))
+        est = eng.empty(Xq.n)
+        fac.mean_at(Xq.t, Xq.ld, Xq.n, est)
+        eng.scatter_col(col, 1, 0, None if need.all() else ridx, est, Xq.n)
+    return fac, block, xd.with_col(col), zd_next
+
+
+def _zd(gpar, x_ind, p):
+    if isinstance(x_ind, DevMat):
+        return DevMat(x_ind.eng, x_ind.t, x_ind.n, x_ind.d, x_ind.ld, frozen=True)
+    return DevMat.from_host(gpar.engine, x_ind, spare=p + 1)
+
+
+def logpdf_sparse(gpar, x, y, w, only_last_layer, return_inputs, x_ind, outputs):
+    eng = gpar.engine
+    if not isinstance(y, dict):
+        y = np.asarray(y, dtype=np.float64)
+        w = np.asarray(w, dtype=np.float64)
+    p = len(gpar.layers)
+    xd = gpar._as_devmat(x, spare=p + 1)
+    zd = _zd(gpar, gpar.x_ind if x_ind is None else x_ind, p)
+    slots = []
+    for is_last, ((y_i, w_i, mask), model) in last(zip(per_output(y, w, keep=gpar.impute), gpar.layers),
+                                                   select=outputs):
+        xd = xd.take_rows(mask)
+        layer = _layer(model)
+        if layer.block is not None:
+            raise NotImplementedError("logpdf under a sparse posterior is not supported yet")
+        fac, _, xd, zd = _train_step(gpar, layer, xd, zd, y_i, w_i, is_last)
+        if (not only_last_layer) or is_last:
+            slots.append((fac.elbo_slot(), fac.n))
+    eng.check_infos()
+    if return_inputs:
+        return xd, zd
+    total = 0.0
+    if slots:
+        vals = torch.stack([s for s, _ in slots]).cpu().numpy()
+        for (t0, t1, t2, _), (_, n) in zip(vals, slots):
+            if n > 0:
+                total += -0.5 * (t0 + t1 - t2)
+    return float(total)
+
+
+def condition_sparse(gpar, out, x, y, w):
+    y = np.asarray(y, dtype=np.float64)
+    w = np.asarray(w, dtype=np.float64)
+    p = y.shape[1]
+    xd = gpar._as_devmat(x, spare=p + 1)
+    zd = _zd(gpar, gpar.x_ind, p)
+    for is_last, ((y_i, w_i, mask), model) in last(zip(per_output(y, w, keep=gpar.impute), gpar.layers)):
+        xd = xd.take_rows(mask)
+        layer = _layer(model)
+        _, block, xd, zd = _train_step(gpar, layer, xd, zd, y_i, w_i, is_last)
+        out.layers.append(construct_model(layer.conditioned(block), layer.noise))
+    gpar.engine.check_infos()
+    return out
+
+
+def sample_sparse(gpar, x, w, latent, num_samples, normals, train, return_device):
+    """model.py:245-277 with sparse posteriors; same contract as :meth:`GPAR.sample`."""
+    eng = gpar.engine
+    S = int(num_samples)
+    p = len(gpar.layers)
+    w = np.asarray(w, dtype=np.float64)
+    xs = gpar._as_devmat(x, spare=p + 1)
+    ns = xs.n
+    if normals is None:
+        Zall = torch.randn(S, p, ns, dtype=F64, device=eng.device)
+        Z2all = torch.randn(S, p, ns, dtype=F64, device=eng.device) if latent else None
+    else:
+        Zall = eng.to_device(np.asarray(normals["Z"], dtype=np.float64).reshape(S, p, ns))
+        Z2all = eng.to_device(np.asarray(normals["Z2"], dtype=np.float64).reshape(S, p, ns)) if latent else None
+    out = eng.empty(max(S * ns * p, 1))
+    shared, xs_all = True, None
+    train_iter = None
+    if train is not None:
+        xt, yt, wt = train
+        yt = np.asarray(yt, dtype=np.float64)
+        wt = np.asarray(wt, dtype=np.float64)
+        xd = gpar._as_devmat(xt, spare=p + 1)
+        zd = _zd(gpar, gpar.x_ind, p)
+        train_iter = per_output(yt, wt, keep=gpar.impute)
+    for i, (is_last, model) in enumerate(last(gpar.layers)):
+        layer = _layer(model)
+        noise = layer.noise
+        sd = eng.to_device(np.sqrt(noise / w[:, i])) if latent else None
+        d_s = eng.zeros(max(ns, 1)) if latent else eng.to_device(noise / w[:, i])
+        Zi = Zall[:, i, :].contiguous()
+        Z2i = Z2all[:, i, :].contiguous() if latent else None
+        fac = None
+        if train_iter is not None:
+            y_i, w_i, mask = next(train_iter)
+            xd = xd.take_rows(mask)
+            fac, _, xd, zd = _train_step(gpar, layer, xd, zd, y_i, w_i, is_last)
+        elif layer.block is not None:
+            blk = layer.block
+            if blk.factor is None:
+                blk.factor = SparseFactor(eng, layer.spec, blk.Z, blk.X, blk.y_host, blk.sig_host)
+            fac = blk.factor
+        if fac is None:
+            # prior layer: dense joint draw (no observations to sparsify)
+            if shared:
+                pf = Factor(eng, layer.spec, xs.t, xs.ld, d_s, eng.zeros(1), 0, ns)
+                f_col = eng.empty(max(S * ns, 1))
+                pf.ext_sample(Zi, S, f_col)
+                y_col = f_col
+                if latent:
+                    y_col = eng.empty(max(S * ns, 1))
+                    pf.ext_sample(Zi, S, y_col, sd=sd, Z2=Z2i)
+                mean = eng.zeros(max(ns, 1))
+            else:
+                f_col, y_col = gpar._chains_layer(layer, None, xs_all, S, ns, d_s, sd, Zi, Z2i, latent)
+                mean = gpar._chain_means
+        elif shared:
+            f_col, y_col, mean = fac.sample_rows(xs, d_s, Zi, S, 1, ns, sd=sd, Z2=Z2i)
+        else:
+            f_col, y_col, mean = fac.sample_rows(xs_all, d_s, Zi, 1, S, ns, sd=sd, Z2=Z2i)
+        eng.scatter_col(out, p, i, None, f_col, S * ns)
+        if not is_last:
+            if gpar.replace:
+                if shared:
+                    xs = xs.with_col(mean)
+                else:
+                    xs_all = xs_all.with_col(mean)
+            else:
+                if shared:
+                    rep = np.tile(np.arange(ns, dtype=np.int64), S)
+                    xs_all = xs.copy_rows(eng.to_device(rep, torch.int64), S * ns, spare=p + 1)
+                    shared = False
+                xs_all = xs_all.with_col(y_col)
+    eng.check_infos()
+    res = out.reshape(S, ns, p)
+    return res if return_device else res.cpu().numpy()

@@ -112,6 +112,20 @@ int gpar_trsm_rows(const double* L, int64_t ldl, int64_t n, const double* ws, do
 int gpar_syrk_sub(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw, int64_t k,
                   int64_t strideW, int64_t batch, void* stream);
 
+/* C_b <- C_b + W_b W_b^T (lower): the `I + B Sigma^-1 B^T` and `+ B_x^T A^-1 B_x'` terms of the VFE
+ * path. */
+int gpar_syrk_add(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw, int64_t k,
+                  int64_t strideW, int64_t batch, void* stream);
+
+/* K8 -- VFE (Titsias) helpers for `PseudoObs` (model.py:286-287).
+ * gpar_transpose_scale: dst (cols x rows) = (diag(scale) src)^T, scale may be NULL.
+ * gpar_vfe_rowterms: out[0] = sum_j (k_jj - ||Bt_j||^2)/sigma_j + log(2 pi sigma_j) + y_j^2/sigma_j
+ * with Bt = K_xz L_z^-T (n x M), the trace / normaliser / data terms of the bound. */
+int gpar_transpose_scale(const double* src, int64_t lds, int64_t rows, int64_t cols, const double* scale,
+                         double* dst, int64_t ldd, void* stream);
+int gpar_vfe_rowterms(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t n, const double* Bt,
+                      int64_t ldb, int64_t M, const double* sigma, const double* y, double* out, void* stream);
+
 /* K3 -- alpha <- L^-T u (u is read only; `work` is n doubles of scratch);
  * out2[0] = 2 sum log L_ii, out2[1] = ||u||^2.  Normal.logpdf tail / iqf. */
 int gpar_backsolve(const double* L, int64_t ldl, int64_t n, const double* ws, const double* u, double* alpha,

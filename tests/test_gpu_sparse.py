@@ -1,0 +1,84 @@
+"""Inducing-point (VFE) path on the GPU vs the oracle's PseudoObs restatement (SURVEY 8a row a9;
+reference tests/test_model.py:118-149 sparse part, BASELINE configs[3] scaled down).  ELBO rel <= 1e-7."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import bench
+from oracle import gpar_oracle as O
+from tests.test_gpu_model import both
+
+pytestmark = pytest.mark.gpu
+
+LAYERS = [
+    ([dict(type="eq", variance=1.0, cols=[0, 1], scales=[0.3, 0.4])], 0.05),
+    ([dict(type="eq", variance=0.8, cols=[0, 1], scales=[0.3, 0.4]),
+      dict(type="linear", variance=1.0, cols=[2], scales=[5.0]),
+      dict(type="eq", variance=0.6, cols=[2], scales=[1.0])], 0.08),
+    ([dict(type="eq", variance=1.1, cols=[0, 1], scales=[0.5, 0.2]),
+      dict(type="linear", variance=1.0, cols=[2, 3], scales=[5.0, 3.0]),
+      dict(type="rq", variance=0.6, cols=[2, 3], scales=[1.0, 2.0], alpha=0.7)], 0.1),
+]
+
+
+def test_sparse_obs_tight_at_z_equals_x():
+    # reference tests/test_model.py:139-149: with x_ind = x the bound equals the exact log-marginal
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((10, 2)); wv = rng.uniform(size=(10, 1)) + 1e-2
+    terms = [dict(type="eq", variance=1.0, cols=[0, 1], scales=[1.0, 1.0])]
+    y = O.GP(terms)(x, 0.1).sample(O.Normals(rng=rng))
+    ym = y.copy(); ym[::2] = np.nan
+    g, _ = both([(terms, 0.1)], x_ind=x)
+    expect = O.GP(terms)(x[1::2], 0.1 / wv[1::2, 0]).logpdf(y[1::2])
+    assert_allclose(g.logpdf(x, ym, wv), expect, atol=1e-6)
+
+
+@pytest.mark.parametrize("replace,impute", [(False, False), (True, True), (False, True)])
+def test_sparse_chain_vs_oracle(replace, impute):
+    rng = np.random.default_rng(7)
+    n, ns, m, p, S, M = 150, 23, 2, 3, 3, 20
+    x = rng.uniform(0, 1, (n, m)); xs = rng.uniform(0, 1, (ns, m)); z = rng.uniform(0, 1, (M, m))
+    g, o = both(LAYERS, replace=replace, impute=impute, x_ind=z)
+    w = rng.uniform(0.5, 2.0, (n, p)); ws = rng.uniform(0.5, 2.0, (ns, p))
+    gen = O.GPAR()
+    for t, nz in LAYERS:
+        gen = gen.add_layer(lambda t=t, nz=nz: (O.GP(t), nz))
+    y = gen.sample(x, w, normals=O.Normals(rng=rng))
+    y[rng.uniform(size=(n, p)) < 0.15] = np.nan
+    a, b = g.logpdf(x, y, w), o.logpdf(x, y, w)
+    assert abs(a - b) <= 1e-7 * abs(b)
+    for latent in (False, True):
+        Z = rng.standard_normal((S, p, ns)); Z2 = rng.standard_normal((S, p, ns))
+        queue = []
+        for s in range(S):
+            for i in range(p):
+                queue.append(Z[s, i])
+                if latent:
+                    queue.append(Z2[s, i])
+        opost = o | (x, y, w)
+        nrm = O.Normals(queue=queue)
+        ref = np.stack([opost.sample(xs, ws, latent=latent, normals=nrm) for _ in range(S)])
+        got = g.sample(xs, ws, latent=latent, num_samples=S, normals={"Z": Z, "Z2": Z2}, train=(x, y, w))
+        assert_allclose(got, ref, rtol=1e-6, atol=1e-7)
+        got2 = (g | (x, y, w)).sample(xs, ws, latent=latent, num_samples=S, normals={"Z": Z, "Z2": Z2})
+        assert_allclose(got2, ref, rtol=1e-6, atol=1e-7)
+
+
+def test_regressor_c4_small():
+    """BASELINE configs[3] (inducing points, linear + nonlinear, replace + impute) at oracle size."""
+    from gpar_b200 import GPARRegressor
+
+    data = bench.make_data(n=500, m=2, p=4, ns=60, S=3, missing=0.1)
+    z = np.random.default_rng(4).uniform(0, 1, (48, 2))
+    kw = dict(scale=0.25, noise=0.1, linear=True, linear_scale=10.0, nonlinear=True, nonlinear_scale=1.0,
+              replace=True, impute=True, normalise_y=True, x_ind=z)
+    reg, ora = GPARRegressor(**kw), O.OracleRegressor(**kw)
+    reg.condition(data["x"], data["y"]); ora.condition(data["x"], data["y"])
+    a, b = reg.logpdf(data["x"], data["y"]), ora.logpdf(data["x"], data["y"])
+    assert abs(a - b) <= 1e-7 * abs(b)
+    S, p = 3, 4
+    mean = reg.predict(data["xs"], num_samples=S, normals={"Z": data["Z"]})
+    queue = [data["Z"][s, i] for s in range(S) for i in range(p)]
+    ref = ora.predict(data["xs"], num_samples=S, normals=O.Normals(queue=queue))
+    assert np.max(np.abs(mean - ref)) <= 1e-5 * np.max(np.abs(ref))
+    assert reg.x_ind.ndim == 2
