@@ -1,0 +1,78 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: chain partition, sharded predict
+(all_reduce of the sample sum) and sharded sample (all_gather, chain order) -- SURVEY 8(e)-1.  The
+per-rank sampler is the oracle here (test infrastructure), so no GPU is needed."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gpar_b200.dist import chain_slice, predict_sharded, sample_sharded, shard_normals
+
+
+def test_chain_slice_partitions_exactly():
+    for S in (0, 1, 2, 7, 100, 256):
+        for world in (1, 2, 3, 8):
+            cover = []
+            for r in range(world):
+                a, b = chain_slice(S, r, world)
+                assert 0 <= a <= b <= S
+                cover.extend(range(a, b))
+            assert cover == list(range(S))
+            sizes = [chain_slice(S, r, world)[1] - chain_slice(S, r, world)[0] for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+    Z = {"Z": np.arange(24).reshape(6, 2, 2), "Z2": np.arange(24).reshape(6, 2, 2) + 100}
+    sl = shard_normals(Z, 2, 5)
+    assert sl["Z"].shape == (3, 2, 2) and sl["Z2"][0, 0, 0] == 108 and shard_normals(None, 0, 1) is None
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, S, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.gpar_oracle import Normals, OracleRegressor
+
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 1, (30, 1)); xs = rng.uniform(0, 1, (9, 1))
+    ora = OracleRegressor(replace=False, impute=False, linear=True, nonlinear=True, noise=0.05, scale=0.3)
+    y = ora.sample(x, p=2, normals=Normals(rng=np.random.default_rng(1)))
+    ora.condition(x, y)
+    Z = np.random.default_rng(2).standard_normal((S, 2, 9))
+
+    def local(start, stop):
+        queue = [Z[s, i] for s in range(start, stop) for i in range(2)]
+        smp = ora.sample(xs, posterior=True, num_samples=stop - start, normals=Normals(queue=queue))
+        return np.stack(smp if isinstance(smp, list) else [smp])
+
+    mean = predict_sharded(None, xs, num_samples=S, local_sampler=local)
+    allsmp = np.stack(sample_sharded(None, xs, num_samples=S, local_sampler=local))
+    if rank == 0:
+        full = local(0, S)
+        q.put((np.abs(mean - full.mean(axis=0)).max(), np.abs(allsmp - full).max(), allsmp.shape))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("S", [5, 8])
+def test_sharded_predict_and_sample_gloo_world2(S):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, S, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    err_mean, err_smp, shape = q.get()
+    assert shape == (S, 9, 2)
+    assert err_mean <= 1e-13 and err_smp == 0.0
