@@ -11,7 +11,7 @@ import os
 import torch  # noqa: F401  (loads libcudart before the CDLL below)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpar_b200.so")
+LIB_PATH = os.environ.get("GPAR_B200_LIB") or os.path.join(_HERE, "libgpar_b200.so")  # env override: kernel experiments only
 
 TILE = 128
 MAX_TERMS = 8

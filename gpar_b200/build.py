@@ -22,16 +22,24 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), suffix=""):
+    """defines/suffix: kernel experiments (e.g. defines=["-DGPAR_STAGES=5"], suffix="_s5" builds
+    libgpar_b200_s5.so next to the product library; select it with GPAR_B200_LIB)."""
+    if suffix:
+        return _build(verbose, list(defines), LIB.replace(".so", suffix + ".so"), "build" + suffix)
     if not force and not _stale():
         return LIB
+    return _build(verbose, [], LIB, "build")
+
+
+def _build(verbose, defines, LIB, bdir):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(os.path.join(HERE, bdir), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(HERE, bdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

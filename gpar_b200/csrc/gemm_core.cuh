@@ -15,7 +15,10 @@ namespace gpar {
 
 constexpr int BK = 16;     // k-chunk
 constexpr int LDSM = 20;   // padded shared row stride (doubles): 160 B keeps 16 B alignment
-constexpr int STAGES = 4;
+#ifndef GPAR_STAGES
+#define GPAR_STAGES 4
+#endif
+constexpr int STAGES = GPAR_STAGES;
 constexpr int GEMM_THREADS = 256;
 
 struct __align__(16) GemmStage {
@@ -139,10 +142,11 @@ __device__ __forceinline__ void gemm_nt_mainloop(GemmStage* stages, const double
   for (int c = 0; c < nchunks; ++c) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
+    mma_chunk<MODE>(stages[c % STAGES], acc, wm, wn, gid, tig, c * BK, mask);
+    // copies after the DMMAs: issued first they queue ahead of the fragment loads (see potrf.cu)
     const int nc = c + STAGES - 1;
     if (nc < nchunks) load_chunk(stages[nc % STAGES], Ap, lda, validA, Bp, ldb, validB, nc * BK, K);
     cp_async_commit();
-    mma_chunk<MODE>(stages[c % STAGES], acc, wm, wn, gid, tig, c * BK, mask);
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -199,9 +203,10 @@ __device__ __forceinline__ void store_tile(double* __restrict__ C, int64_t ldc, 
   }
 }
 
-// C = C2 + acc (C2 is a dense tile with leading dimension ldc2).
-__device__ __forceinline__ void store_tile_add(double* __restrict__ C, int64_t ldc, const double* __restrict__ C2,
-                                               int64_t ldc2, int rows, int cols, const Acc& acc) {
+// acc += C2 (a dense tile with leading dimension ldc2, written earlier by store_tile<0> of the
+// same thread layout: every thread re-reads exactly the elements it stored).
+__device__ __forceinline__ void acc_add_tile(Acc& acc, const double* __restrict__ C2, int64_t ldc2, int rows,
+                                             int cols) {
   const int warp = canonical_warp(), lane = threadIdx.x & 31;
   const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
 #pragma unroll
@@ -211,8 +216,8 @@ __device__ __forceinline__ void store_tile_add(double* __restrict__ C, int64_t l
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = wn * 64 + j * 8 + 2 * tig;
-      if (c < cols) C[(int64_t)r * ldc + c] = C2[(int64_t)r * ldc2 + c] + acc[i][j][0];
-      if (c + 1 < cols) C[(int64_t)r * ldc + c + 1] = C2[(int64_t)r * ldc2 + c + 1] + acc[i][j][1];
+      if (c < cols) acc[i][j][0] += C2[(int64_t)r * ldc2 + c];
+      if (c + 1 < cols) acc[i][j][1] += C2[(int64_t)r * ldc2 + c + 1];
     }
   }
 }

@@ -20,296 +20,426 @@ namespace gpar {
 // --------------------------------------------------------------------------------------
 constexpr int DLD = 132;  // row stride of the tile in shared memory: = 4 (mod 16) doubles makes the DMMA
                           // fragment loads bank-conflict free; rows stay 16-byte aligned for cp.async
+constexpr int PANEL = 32; // panel width of the in-tile blocked factorisation
 constexpr double REFINE_KAPPA = 1.0e3;  // kappa_inf(L_kk) above which the tile solves are refined
-constexpr size_t DIAG_SMEM_BYTES = sizeof(double) * (TILE * DLD + TILE + 32) + 16;
+// shared layout: Ls[TILE][DLD] | rdiag[TILE] | LT[PANEL][PANEL] | red[32] | ints
+constexpr size_t DIAG_SMEM_BYTES = sizeof(double) * (TILE * DLD + TILE + PANEL * PANEL + 32) + 16;
 
-// Factor one diagonal tile in shared memory (all 256 threads of the CTA).  Atile points at
-// A[j0][j0]; on return the tile holds L_kk (strictly upper part zeroed), ws its inverse,
-// *flag_out the refinement flag, *info_b the first bad pivot (if none was recorded before).
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// Load the lower triangle of a diagonal tile into Ls (zeros above the diagonal, identity padding
+// beyond kb).  All 256 threads; ends with a barrier.
+__device__ __forceinline__ void diag_load(unsigned char* smem_raw, const double* __restrict__ Atile, int64_t lda,
+                                          int kb) {
+  double* Ls = reinterpret_cast<double*>(smem_raw);
+  const int tid = threadIdx.x;
+  const bool vec_ok = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(Atile) & 15) == 0);
+  if (vec_ok) {
+    // zero-filling copies: 16 B below the diagonal, 8 B on it, 0 B (pure zero fill) above / beyond kb
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+      const int idx = tid + q * 256;  // 0..8191: row r, double2 column c
+      const int r = idx >> 6, c = (idx & 63) * 2;
+      const int bytes = (r < kb) ? ((c + 1 <= r) ? 16 : ((c == r) ? 8 : 0)) : 0;
+      cp_async16(&Ls[r * DLD + c], bytes ? (Atile + (int64_t)r * lda + c) : Atile, bytes);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  } else {
+    for (int idx = tid; idx < TILE * TILE; idx += 256) {
+      const int r = idx >> 7, c = idx & 127;
+      Ls[r * DLD + c] = (r < kb && c <= r) ? __ldcg(Atile + (int64_t)r * lda + c) : 0.0;
+    }
+  }
+  __syncthreads();
+  if (tid >= kb && tid < TILE) Ls[tid * DLD + tid] = 1.0;  // identity padding
+  __syncthreads();
+}
+
+// Explicit shared-space accesses for the latency-critical panel routines: with generic pointers the
+// compiler re-derives the shared window base (S2UR SR_CgaCtaId) after every barrier / __syncwarp,
+// which sits right on the pivot chain.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v2f64(uint32_t a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+// 1 / sqrt(x) for a normal positive x: MUFU.RSQ64H seed (2^-22) + one third-order correction, the
+// same arithmetic as the CUDA library routine without its special-case branch (pivots that are
+// not positive normal numbers were replaced before this is called).
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y0) : "d"(x));
+  const double e = fma(-(y0 * y0), x, 1.0);
+  const double pp = fma(e, 0.375, 0.5);
+  const double ye = y0 * e;
+  return fma(pp, ye, y0);
+}
+
+// Warp 0 of a panel step: Cholesky of the 32 x 32 diagonal block at (c0, c0), one ROW per lane in
+// registers, right-looking.  Per column: the pivot travels by one shuffle, every lane takes the
+// rsqrt redundantly, scales its entry, and the rank-1 update reads L[l][j] back from the published
+// column (broadcast shared loads; shuffling every operand is scoreboard-bound, 3x slower).
+// The next pivot is updated first (own-lane operands only), so the dependent chain per column is
+// shuffle -> rsqrt -> mul -> fma.  Column j is published transposed (LT[j][i] = L[i][j], conflict
+// free) with rdiag[c0 + j] = 1 / L_jj; every 8 columns the warp arrives on named barrier 1 + j/8,
+// on which the row-solving warps wait.  Returns the 1-based index of the first bad pivot (or 0).
+__device__ __forceinline__ int factor32_warp(double* __restrict__ Ls, double* __restrict__ rdiag,
+                                             double* __restrict__ LT, int c0, int lane) {
+  double a[PANEL];
+  const uint32_t row = smem_u32(Ls + (c0 + lane) * DLD + c0);
+  const uint32_t lt = smem_u32(LT);
+  const uint32_t rd = smem_u32(rdiag + c0);
+#pragma unroll
+  for (int q = 0; q < PANEL / 2; ++q) {
+    const double2 v = lds_v2f64(row + 16 * q);
+    a[2 * q] = v.x;
+    a[2 * q + 1] = v.y;
+  }
+  int bad = 0;
+  double piv = __shfl_sync(0xffffffffu, a[0], 0);
+#pragma unroll
+  for (int j = 0; j < PANEL; ++j) {
+    if (!(piv > 1.0e-300) || piv > 1.0e300) {
+      if (bad == 0) bad = j + 1;
+      piv = 1.0;
+    }
+    const double rs = rsqrt_pos(piv);
+    const double lij = ((lane == j) ? piv : a[j]) * rs;  // lane j: sqrt(piv); lanes > j: L[i][j]
+    sts_f64(lt + 8 * (j * PANEL + lane), lij);
+    sts_f64(row + 8 * j, lij);  // L[i][j] into the tile.  Lanes < j drop garbage into the strict upper part of
+                                // the block, which the identity-row warp overwrites after the last barrier.
+    if (lane == j) sts_f64(rd + 8 * j, rs);
+    if (j + 1 < PANEL) {
+      const double dn = fma(-lij, lij, a[j + 1]);  // next pivot (meaningful in lane j + 1)
+      piv = __shfl_sync(0xffffffffu, dn, j + 1);
+    }
+    __syncwarp();  // column j is visible to the whole warp
+    if (j + 1 < PANEL) {
+      // rank-1 update: L[l][j] comes back from the published column as broadcast loads (the pivot
+      // chain above does not wait for them)
+      const uint32_t col = lt + 8 * (j * PANEL);
+      int l = j + 1;
+      if (l & 1) {
+        a[l] = fma(-lij, lds_f64(col + 8 * l), a[l]);
+        ++l;
+      }
+#pragma unroll
+      for (; l < PANEL; l += 2) {
+        const double2 t = lds_v2f64(col + 8 * l);
+        a[l] = fma(-lij, t.x, a[l]);
+        a[l + 1] = fma(-lij, t.y, a[l + 1]);
+      }
+    }
+    a[j] = lij;
+    if ((j & 7) == 7) named_bar_arrive(1 + (j >> 3), 160);
+  }
+  return bad;
+}
+
+// Warps 1-4 of a panel step: row r of the tile (one row per lane) is solved against the 32 x 32
+// block, x L32^T = t, by right-looking substitution as the columns are published (backward
+// stable, no inverse involved).  Rows above the panel are inverse rows (their entries live in the
+// strict upper triangle), rows inside the panel start as identity rows (the inverse of the block
+// itself falls out), rows below are rows of L.
+__device__ __forceinline__ void panel_solve_warp(double* __restrict__ Ls, const double* __restrict__ rdiag,
+                                                 const double* __restrict__ LT, int c0, int r) {
+  double x[PANEL];
+  const uint32_t row = smem_u32(Ls + r * DLD + c0);
+  const uint32_t lt = smem_u32(LT);
+  const uint32_t rd = smem_u32(rdiag + c0);
+  const bool inblk = (r >= c0) && (r < c0 + PANEL);
+#pragma unroll
+  for (int q = 0; q < PANEL / 2; ++q) {
+    const double2 v = lds_v2f64(row + 16 * q);
+    x[2 * q] = v.x;
+    x[2 * q + 1] = v.y;
+  }
+  if (inblk) {
+#pragma unroll
+    for (int j = 0; j < PANEL; ++j) x[j] = (j == r - c0) ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < PANEL; ++j) {
+    if ((j & 7) == 0) named_bar_sync(1 + (j >> 3), 160);
+    const double xj = x[j] * lds_f64(rd + 8 * j);
+    x[j] = xj;
+    const uint32_t col = lt + 8 * (j * PANEL);  // col[l] = L[l][j]
+    int l = j + 1;
+    if (l & 1) {
+      if (l < PANEL) x[l] = fma(-xj, lds_f64(col + 8 * l), x[l]);
+      ++l;
+    }
+#pragma unroll
+    for (; l < PANEL; l += 2) {
+      const double2 v = lds_v2f64(col + 8 * l);
+      x[l] = fma(-xj, v.x, x[l]);
+      x[l + 1] = fma(-xj, v.y, x[l + 1]);
+    }
+  }
+  if (!inblk) {
+#pragma unroll
+    for (int q = 0; q < PANEL / 2; ++q) sts_v2f64(row + 16 * q, x[2 * q], x[2 * q + 1]);
+  } else {
+    // the diagonal entry is rdiag (already there) and the lower part holds L32: strict upper only
+#pragma unroll
+    for (int j = 0; j < PANEL; ++j)
+      if (j > r - c0) sts_f64(row + 8 * j, x[j]);
+  }
+}
+
+// Rank-32 trailing update of the columns beyond panel p (all 8 warps): C -= X_panel L_panel^T on the
+// inverse rows (rows < c0 + 32, strict-upper region) and on the lower part of the L rows.  Work
+// unit = 16 rows x 32 columns (2 x 4 DMMA tiles, K = 32), dealt round-robin to the warps.
+__device__ __forceinline__ void rank32_update(double* __restrict__ Ls, const double* __restrict__ rdiag, int p,
+                                              int warp, int gid, int tig) {
+  const int c0 = PANEL * p;
+  int u = 0;
+  for (int rb = 0; rb < TILE / 16; ++rb) {
+    const int R0 = 16 * rb;
+    const bool lrows = R0 >= c0 + PANEL;
+    const bool inblk = (R0 >= c0) && !lrows;
+    for (int cb = p + 1; cb < TILE / PANEL; ++cb) {
+      if (lrows && PANEL * cb > R0 + 15) continue;
+      if ((u++ & 7) != warp) continue;
+      const int C0 = PANEL * cb;
+      double af[2][8], bf[4][8], cf[2][4][2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int r = R0 + 8 * t + gid;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const int kk = 4 * ks + tig;
+          double v = Ls[r * DLD + c0 + kk];
+          if (inblk) v = (kk > r - c0) ? v : ((kk == r - c0) ? rdiag[r] : 0.0);
+          af[t][ks] = -v;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) bf[q][ks] = Ls[(C0 + 8 * q + gid) * DLD + c0 + 4 * ks + tig];
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double2 v = *reinterpret_cast<const double2*>(Ls + (R0 + 8 * t + gid) * DLD + C0 + 8 * q + 2 * tig);
+          cf[t][q][0] = v.x;
+          cf[t][q][1] = v.y;
+        }
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dmma884(cf[t][q][0], cf[t][q][1], af[t][ks], bf[q][ks]);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int rt = 2 * rb + t, ct = 4 * cb + q;
+          double* pc = Ls + (R0 + 8 * t + gid) * DLD + C0 + 8 * q + 2 * tig;
+          if (!lrows || ct < rt) {
+            *reinterpret_cast<double2*>(pc) = make_double2(cf[t][q][0], cf[t][q][1]);
+          } else if (ct == rt) {  // diagonal sub-tile: its strict upper part belongs to the inverse rows
+            if (2 * tig <= gid) pc[0] = cf[t][q][0];
+            if (2 * tig + 1 <= gid) pc[1] = cf[t][q][1];
+          }
+        }
+    }
+  }
+}
+
+// Factor the diagonal tile held in Ls (see diag_load / assemble_diag) -- all 256 threads.  On
+// return the tile L_kk (strictly upper part of each 32 x 32 diagonal block zeroed) is in Atile, its
+// inverse in ws, *flag_out holds the refinement flag, *info_b the first bad pivot (if none was
+// recorded before).  When ready_flag != nullptr it is released as soon as everything a consumer
+// reads is in global memory: after Linv for well-conditioned tiles (only the refined solves read
+// L_kk), after L_kk otherwise.
 //
-// Right-looking sweep over 16 column blocks of width 8 on ONE 128 x 129 shared array:
-//   lower triangle  = L (in place);
-//   strict upper    = the appended identity rows of the sweep, i.e. (I L^-T)[r][c] = Linv[c][r]
-//                     (the diagonal of Linv is rdiag = 1 / L_rr), so the inverse costs no extra
-//                     phase and no extra storage.
-// Per block: (a) warps 0-3: every thread factors the 8x8 diagonal block redundantly in registers
-// (chain = 8 x (rsqrt + mul + fma), no communication), (b) thread r solves row r against it by
-// substitution (backward stable: no refinement needed), (c) all warps apply the rank-8 trailing
-// update with DMMA (independent 8x8 sub-tiles, no accumulate chains).
-__device__ __forceinline__ void diag_factor_tile(unsigned char* smem_raw, double* __restrict__ Atile, int64_t lda,
+// One 128 x 132 shared array: lower triangle = L (in place); strict upper = the appended identity
+// rows of the sweep, (I L^-T)[r][c] = Linv[c][r] (the diagonal of Linv is rdiag = 1 / L_rr), so the
+// inverse costs no extra phase.  Four panel steps of width 32: warp 0 factors the diagonal block
+// (shuffle pivots, registers), warps 1-4 solve the 128 rows against it as its columns appear, then
+// all warps apply the rank-32 DMMA update to the columns beyond the panel.
+__device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* __restrict__ Atile, int64_t lda,
                                                  int kb, int64_t j0, double* __restrict__ ws,
                                                  double* __restrict__ flag_out, int32_t* __restrict__ info_b,
-                                                 long long* prof = nullptr) {
+                                                 int* ready_flag, long long* prof) {
 #define GPAR_PROF(i) do { if (prof && threadIdx.x == 0) prof[i] = clock64(); } while (0)
-  GPAR_PROF(0);
   double* Ls = reinterpret_cast<double*>(smem_raw);
   double* rdiag = Ls + TILE * DLD;
-  double* red = rdiag + TILE;  // 32 doubles of reduction scratch
-  int* s_bad = reinterpret_cast<int*>(red + 32);
+  double* LT = rdiag + TILE;
+  double* red = LT + PANEL * PANEL;  // 32 doubles of reduction scratch
+  int* s_int = reinterpret_cast<int*>(red + 32);  // [0] first bad pivot, [1] refine
   const int tid = threadIdx.x, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
   const int warp = canonical_warp();
-
-  // ---- load the lower triangle with cp.async (16-byte, all in flight), then fix up: zeros above
-  // the diagonal, identity padding beyond kb ------------------------------------------------------
-  {
-    const bool vec_ok = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(Atile) & 15) == 0);
-    if (vec_ok) {
-      // zero-filling copies: 16 B below the diagonal, 8 B on it, 0 B (pure zero fill) above / beyond kb
-#pragma unroll 8
-      for (int q = 0; q < 32; ++q) {
-        const int idx = tid + q * 256;  // 0..8191: row r, double2 column c
-        const int r = idx >> 6, c = (idx & 63) * 2;
-        const int bytes = (r < kb) ? ((c + 1 <= r) ? 16 : ((c == r) ? 8 : 0)) : 0;
-        cp_async16(&Ls[r * DLD + c], bytes ? (Atile + (int64_t)r * lda + c) : Atile, bytes);
-      }
-      cp_async_commit();
-      cp_async_wait<0>();
-    } else {
-      for (int idx = tid; idx < TILE * TILE; idx += 256) {
-        const int r = idx >> 7, c = idx & 127;
-        Ls[r * DLD + c] = (r < kb && c <= r) ? __ldcg(Atile + (int64_t)r * lda + c) : 0.0;
-      }
-    }
-    __syncthreads();
-    if (tid >= kb && tid < TILE) Ls[tid * DLD + tid] = 1.0;  // identity padding
-  }
-  if (tid == 0) *s_bad = 0;
-  __syncthreads();
+  if (tid == 0) s_int[0] = 0;
   GPAR_PROF(1);
-
-  // Warp 0: factor the 8x8 diagonal block kblk in registers (all lanes redundantly: the chain is
-  // 8 x (rsqrt + mul + fma) with no communication); lanes 0-7 publish row m of L8 and 1 / L_mm.
-  auto factor_block = [&](int kblk) {
-    const int c0 = 8 * kblk;
-    double d[8][8], rd[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j <= i; ++j) d[i][j] = Ls[(c0 + i) * DLD + c0 + j];
-    int bad = 0;
-    if (kblk == 1) GPAR_PROF(13);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      double piv = d[j][j];
-      if (!(piv > 0.0)) {
-        if (bad == 0) bad = j + 1;
-        piv = 1.0;
-      }
-      const double rs = rsqrt(piv);
-      rd[j] = rs;
-      d[j][j] = piv * rs;
-#pragma unroll
-      for (int i = j + 1; i < 8; ++i) d[i][j] *= rs;
-#pragma unroll
-      for (int i = j + 1; i < 8; ++i)
-#pragma unroll
-        for (int l = j + 1; l <= i; ++l) d[i][l] = fma(-d[i][j], d[l][j], d[i][l]);
-    }
-    if (kblk == 1) GPAR_PROF(14);
-    // publish without divergent branches: predicated stores, lane mm writes row mm
-#pragma unroll
-    for (int mm = 0; mm < 8; ++mm) {
-#pragma unroll
-      for (int j = 0; j <= mm; ++j) {
-        const double v = d[mm][j];
-        if (lane == mm) Ls[(c0 + mm) * DLD + c0 + j] = v;
-      }
-      const double rv = rd[mm];
-      if (lane == mm) rdiag[c0 + mm] = rv;
-    }
-    if (bad && lane == 0 && *s_bad == 0) *s_bad = c0 + bad;
-  };
-
-  if (warp == 0) factor_block(0);
 #pragma unroll 1
-  for (int k = 0; k < TILE / 8; ++k) {
-    const int c0 = 8 * k;
-    __syncthreads();  // L8(k) published; trailing update of step k-1 complete
-    if (k == 0 || k == 8) GPAR_PROF(2 + (k ? 6 : 0));
-    if (warp < 4) {
-      // row r = tid: x L8^T = t by substitution against the published block (backward stable)
-      double d[8][8], rd[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        rd[i] = rdiag[c0 + i];
-#pragma unroll
-        for (int j = 0; j < i; ++j) d[i][j] = Ls[(c0 + i) * DLD + c0 + j];
-      }
-      const int r = tid;
-      const bool in_block = (r >= c0 && r < c0 + 8);
-      double x[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = in_block ? ((r - c0 == j) ? 1.0 : 0.0) : Ls[r * DLD + c0 + j];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        double sacc = x[j];
-#pragma unroll
-        for (int i = 0; i < j; ++i) sacc = fma(-x[i], d[j][i], sacc);
-        x[j] = sacc * rd[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j)  // in-block rows keep L8 in their lower part: only the strict upper is theirs
-        if (!in_block || j > r - c0) Ls[r * DLD + c0 + j] = x[j];
-    }
-    if (k == 0 || k == 8) GPAR_PROF(3 + (k ? 6 : 0));
-    __syncthreads();
-    if (k == 0 || k == 8) GPAR_PROF(4 + (k ? 6 : 0));
-    if (k == TILE / 8 - 1) break;
-    // rank-8 trailing update C -= X X^T.  Column tile ct > k meets row tiles rt in [0, k] (inverse
-    // rows, strict-upper region) and rt in [ct, 15] (L rows).  Warp 0 takes the next diagonal
-    // sub-tile and factors it right away (look-ahead); warps 1-7 share the other row tiles and
-    // process four column tiles at a time (independent accumulators).
+  for (int p = 0; p < TILE / PANEL; ++p) {
+    const int c0 = PANEL * p;
+    __syncthreads();  // the tile (or the previous rank-32 update) is complete
     if (warp == 0) {
-      const int row = (k + 1) * 8 + gid;
-      const double a0 = Ls[row * DLD + c0 + tig], a1 = Ls[row * DLD + c0 + 4 + tig];
-      double* pc = Ls + row * DLD + (k + 1) * 8 + 2 * tig;
-      double c0v = pc[0], c1v = pc[1];
-      dmma884(c0v, c1v, -a0, a0);
-      dmma884(c0v, c1v, -a1, a1);
-      if (2 * tig <= gid) pc[0] = c0v;
-      if (2 * tig + 1 <= gid) pc[1] = c1v;
-      __syncwarp();
-      if (k == 0 || k == 8) GPAR_PROF(5 + (k ? 6 : 0));
-      factor_block(k + 1);
-      if (k == 0 || k == 8) GPAR_PROF(6 + (k ? 6 : 0));
-    } else {
-      if (prof && k == 0 && tid == 32) prof[15] = clock64();
-      int unit = 0;
-      for (int rt = 0; rt < TILE / 8; ++rt) {
-        if (rt == k + 1) continue;
-        const int ct_lo = k + 1, ct_hi = (rt <= k) ? (TILE / 8 - 1) : rt;  // inclusive
-        const int nunits = (ct_hi - ct_lo + 4) / 4;
-        // does this warp own any (rt, batch) unit?  units are dealt round-robin to warps 1..7
-        const int first = (warp - 1 - unit % 7 + 7) % 7;  // offset of my first unit within this row tile
-        const int ubase = unit;
-        unit += nunits;
-        if (first >= nunits) continue;
-        (void)ubase;
-        const int row = rt * 8 + gid;
-        double a0, a1;
-        if (rt == k) {  // inverse rows of the current block: strict upper stored, diagonal = rdiag
-          a0 = (tig > gid) ? Ls[row * DLD + c0 + tig] : ((tig == gid) ? rdiag[row] : 0.0);
-          a1 = (tig + 4 > gid) ? Ls[row * DLD + c0 + 4 + tig] : ((tig + 4 == gid) ? rdiag[row] : 0.0);
-        } else {
-          a0 = Ls[row * DLD + c0 + tig];
-          a1 = Ls[row * DLD + c0 + 4 + tig];
-        }
-        a0 = -a0;
-        a1 = -a1;
-        for (int ctb = ct_lo + 4 * first; ctb <= ct_hi; ctb += 28) {
-          double b0[4], b1[4], cv[4][2];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int ct = min(ctb + u, ct_hi);
-            b0[u] = Ls[(ct * 8 + gid) * DLD + c0 + tig];
-            b1[u] = Ls[(ct * 8 + gid) * DLD + c0 + 4 + tig];
-            const double* pc = Ls + row * DLD + ct * 8 + 2 * tig;
-            cv[u][0] = pc[0];
-            cv[u][1] = pc[1];
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) dmma884(cv[u][0], cv[u][1], a0, b0[u]);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) dmma884(cv[u][0], cv[u][1], a1, b1[u]);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int ct = ctb + u;
-            if (ct > ct_hi) continue;
-            double* pc = Ls + row * DLD + ct * 8 + 2 * tig;
-            if (rt == ct) {  // diagonal sub-tile: its strict upper part belongs to the inverse rows
-              if (2 * tig <= gid) pc[0] = cv[u][0];
-              if (2 * tig + 1 <= gid) pc[1] = cv[u][1];
-            } else {
-              pc[0] = cv[u][0];
-              pc[1] = cv[u][1];
-            }
-          }
-        }
-      }
-      if (prof && k == 0 && tid == 32) prof[16] = clock64();
-    }
-  }
-  GPAR_PROF(19);
-
-  // ---- kappa_inf(L_kk) = ||L||_inf ||Linv||_inf decides refinement: two threads per row ------
-  {
-    const int r = tid >> 1, h = tid & 1;
-    double rowL = 0.0, rowI = 0.0;
-    if (r < kb) {
-      // row r of L: columns [0, r]; row r of Linv: Linv[r][c] = Ls[c][r] for c < r, rdiag[r] at c = r
-      const int lo = h ? (r + 1) / 2 : 0, hi = h ? r : (r + 1) / 2;
-#pragma unroll 8
-      for (int c = lo; c < hi; ++c) {
-        rowL += fabs(Ls[r * DLD + c]);
-        rowI += fabs(Ls[c * DLD + r]);
-      }
-      if (h) {
-        rowL += fabs(Ls[r * DLD + r]);
-        rowI += fabs(rdiag[r]);
-      }
-    }
-    rowL += __shfl_xor_sync(0xffffffffu, rowL, 1);
-    rowI += __shfl_xor_sync(0xffffffffu, rowI, 1);
-#pragma unroll
-    for (int off = 16; off > 1; off >>= 1) {
-      rowL = fmax(rowL, __shfl_xor_sync(0xffffffffu, rowL, off));
-      rowI = fmax(rowI, __shfl_xor_sync(0xffffffffu, rowI, off));
-    }
-    if (lane == 0) {
-      red[warp] = rowL;
-      red[8 + warp] = rowI;
+      const int bad = factor32_warp(Ls, rdiag, LT, c0, lane);
+      if (bad && lane == 0 && s_int[0] == 0) s_int[0] = c0 + bad;
+      if (prof && lane == 0) prof[16 + p] = clock64();
+    } else if (warp <= 4) {
+      panel_solve_warp(Ls, rdiag, LT, c0, (warp - 1) * 32 + lane);
+      if (prof && lane == 0 && (warp == 1 || warp == 4)) prof[(warp == 1 ? 20 : 24) + p] = clock64();
     }
     __syncthreads();
-    if (tid == 0) {
-      double mL = 0.0, mI = 0.0;
-      for (int i = 0; i < 8; ++i) {
-        mL = fmax(mL, red[i]);
-        mI = fmax(mI, red[8 + i]);
-      }
-      const double kappa = mL * mI;
-      *flag_out = (kappa > REFINE_KAPPA || !(kappa == kappa)) ? 1.0 : 0.0;
-    }
+    GPAR_PROF(2 + 2 * p);
+    if (p + 1 < TILE / PANEL) rank32_update(Ls, rdiag, p, warp, gid, tig);
+    GPAR_PROF(3 + 2 * p);
   }
-  // ---- write back L and Linv (row major, ld = 128).  Only the lower triangles are stored, plus
-  // zeros in the strictly upper part of each 32x32 diagonal block: every consumer (MODE 2 GEMMs
-  // skip whole 32-column halves per k-chunk, backsolve starts at the 8x8 diagonal block) stays
-  // inside that region, so nothing else is ever read. -----------------------------------------------
+  __syncthreads();
+  GPAR_PROF(10);
+
+  // ---- ||L||_inf: warp per row, lanes along the columns; the 16 rows of a warp are reduced with
+  // independent shuffle chains ----------------------------------------------------------------------
+  {
+    double srow[TILE / 8];
+#pragma unroll
+    for (int it = 0; it < TILE / 8; ++it) {
+      const int r = warp + 8 * it, c = 4 * lane;
+      double sv = 0.0;
+      if (c <= r) {
+        const double2 v0 = *reinterpret_cast<const double2*>(Ls + r * DLD + c);
+        const double2 v1 = *reinterpret_cast<const double2*>(Ls + r * DLD + c + 2);
+        sv = fabs(v0.x) + ((c + 1 <= r) ? fabs(v0.y) : 0.0) + ((c + 2 <= r) ? fabs(v1.x) : 0.0) +
+             ((c + 3 <= r) ? fabs(v1.y) : 0.0);
+      }
+      srow[it] = sv;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int it = 0; it < TILE / 8; ++it) srow[it] += __shfl_xor_sync(0xffffffffu, srow[it], off);
+    double mL = 0.0;
+#pragma unroll
+    for (int it = 0; it < TILE / 8; ++it) mL = fmax(mL, srow[it]);  // rows >= kb are identity rows: harmless
+    if (lane == 0) red[warp] = mL;
+  }
+  GPAR_PROF(13);
+  // ---- Linv (row major, ld = 128) and its row sums.  Linv[r][c] = Ls[c][r] (c < r), rdiag[r] at
+  // c = r, zeros up to the end of the 32 x 32 diagonal block.  Lanes run along r (two lanes per
+  // shared bank: conflict free at stride 132), every lane assembles 4 consecutive c = one 32-byte
+  // sector of the output.  Unit = (32-row block rb, column group cg), 80 units over the 8 warps. --
+  {
+    double isum[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int it = 0; it < 10; ++it) {
+      const int u = warp + 8 * it;
+      const int rb = (u < 8) ? 0 : ((u < 24) ? 1 : ((u < 48) ? 2 : 3));
+      const int cg = u - ((rb == 0) ? 0 : ((rb == 1) ? 8 : ((rb == 2) ? 24 : 48)));
+      const int r = 32 * rb + lane, c = 4 * cg;
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double off = Ls[(c + q) * DLD + r];
+        v[q] = (c + q < r) ? off : ((c + q == r) ? rdiag[r] : 0.0);
+      }
+      if (r < kb) {
+        double* dst = ws + r * TILE + c;
+        *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
+        const double s = (fabs(v[0]) + fabs(v[1])) + (fabs(v[2]) + fabs(v[3]));
+        if (rb == 0) isum[0] += s; else if (rb == 1) isum[1] += s; else if (rb == 2) isum[2] += s; else isum[3] += s;
+      }
+    }
+    // partial row sums of this warp -> LT scratch [8][128]
+#pragma unroll
+    for (int rb = 0; rb < 4; ++rb) LT[warp * TILE + 32 * rb + lane] = isum[rb];
+  }
+  GPAR_PROF(14);
+  __syncthreads();
+  if (tid < TILE) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += LT[w * TILE + tid];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, off));
+    if (lane == 0) red[8 + warp] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mL = 0.0, mI = 0.0;
+    for (int i = 0; i < 8; ++i) mL = fmax(mL, red[i]);
+    for (int i = 0; i < 4; ++i) mI = fmax(mI, red[8 + i]);
+    const double kappa = mL * mI;
+    const int refine = (kappa > REFINE_KAPPA || !(kappa == kappa)) ? 1 : 0;
+    *flag_out = refine ? 1.0 : 0.0;
+    s_int[1] = refine;
+    if (s_int[0] != 0 && *info_b == 0) *info_b = static_cast<int32_t>(j0) + s_int[0];
+  }
+  __threadfence();
+  __syncthreads();
+  const bool refine = s_int[1] != 0;
+  if (ready_flag && !refine && tid == 0) st_release(ready_flag, 1);
+  GPAR_PROF(11);
+  // ---- L (row major).  Only the lower triangle is stored, plus zeros in the strictly upper part of
+  // each 32 x 32 diagonal block: every consumer (MODE 2 GEMMs skip whole 32-column halves per
+  // k-chunk, backsolve starts at the 8 x 8 diagonal block) stays inside that region. ----------------
   {
     const bool vec_ok = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(Atile) & 15) == 0);
+    const int c = 4 * lane;
 #pragma unroll 4
-    for (int idx = tid; idx < TILE * (TILE / 2); idx += 256) {  // L: row-wise, conflict free
-      const int r = idx >> 6, c = (idx & 63) * 2;
-      if (r >= kb || c > (r | 31) || c >= kb) continue;  // keep zeros in the 32x32 diagonal blocks
-      double2 lv = make_double2(0.0, 0.0);
-      if (c <= r) lv.x = Ls[r * DLD + c];
-      if (c + 1 <= r) lv.y = Ls[r * DLD + c + 1];
+    for (int r = warp; r < kb; r += 8) {
+      if (c > (r | 31) || c >= kb) continue;
+      const double2 v0 = *reinterpret_cast<const double2*>(Ls + r * DLD + c);
+      const double2 v1 = *reinterpret_cast<const double2*>(Ls + r * DLD + c + 2);
+      double v[4] = {v0.x, v0.y, v1.x, v1.y};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (c + q > r) v[q] = 0.0;
       double* dst = Atile + (int64_t)r * lda + c;
-      if (vec_ok && c + 1 < kb) {
-        *reinterpret_cast<double2*>(dst) = lv;
+      if (vec_ok && c + 3 < kb) {
+        *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
       } else {
-        dst[0] = lv.x;
-        if (c + 1 < kb) dst[1] = lv.y;
-      }
-    }
-    // Linv[r][c] = Ls[c][r] (c < r): transposed read.  A warp moves an 8 (r) x 4 (c) block per step
-    // with lanes laid out so that (4 c + r) mod 16 is distinct within each half warp (conflict free
-    // at stride 132); the 4 consecutive c of a row form one 32-byte sector of the output.
-    {
-      const int rr = (lane & 3) + 4 * (lane >> 4), cc = (lane >> 2) & 3;
-#pragma unroll 4
-      for (int blk = warp; blk < (TILE / 8) * (TILE / 4); blk += 8) {
-        const int R0 = (blk >> 5) * 8, C0 = (blk & 31) * 4;
-        if (C0 > (R0 | 31)) continue;
-        const int r = R0 + rr, c = C0 + cc;
-        if (r >= kb) continue;
-        double v = 0.0;
-        if (c < r) v = Ls[c * DLD + r]; else if (c == r) v = rdiag[r];
-        ws[r * TILE + c] = v;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (c + q < kb) dst[q] = v[q];
       }
     }
   }
-  if (tid == 0 && *s_bad != 0 && *info_b == 0) *info_b = static_cast<int32_t>(j0) + *s_bad;
-  GPAR_PROF(20);
+  if (ready_flag && refine) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release(ready_flag, 1);
+  }
+  GPAR_PROF(12);
 #undef GPAR_PROF
 }
 
@@ -321,8 +451,11 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, 
   const int64_t j0 = (int64_t)kt * TILE;
   const int kb = static_cast<int>(min64(TILE, n - j0));
   double* wsb = ws + (int64_t)b * strideWs;
-  diag_factor_tile(smem_raw, A + (int64_t)b * strideA + j0 * lda + j0, lda, kb, j0, wsb + (int64_t)kt * TILE * TILE,
-                   wsb + (int64_t)nt_total * TILE * TILE + kt, info + b, prof);
+  double* Atile = A + (int64_t)b * strideA + j0 * lda + j0;
+  if (prof && threadIdx.x == 0) prof[0] = clock64();
+  diag_load(smem_raw, Atile, lda, kb);
+  diag_factor_core(smem_raw, Atile, lda, kb, j0, wsb + (int64_t)kt * TILE * TILE,
+                   wsb + (int64_t)nt_total * TILE * TILE + kt, info + b, nullptr, prof);
 }
 
 // --------------------------------------------------------------------------------------
@@ -330,11 +463,10 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, 
 // --------------------------------------------------------------------------------------
 // X = T L_kk^-T for one 128-row tile: X0 = T Linv^T; when the diagonal block is flagged
 // ill-conditioned, one refinement step R = T - X0 L_kk^T, X = X0 + R Linv^T (X0 parked in a
-// per-CTA scratch tile) restores backward stability.
+// per-CTA scratch tile) restores backward stability.  On return T holds X and so does `acc`.
 __device__ __forceinline__ void tile_solve(GemmStage* stages, double* __restrict__ T, int64_t ldt, int valid, int kb,
                                            const double* __restrict__ Linv, const double* __restrict__ Lkk,
-                                           int64_t ldl, bool refine, double* __restrict__ scratch) {
-  Acc acc;
+                                           int64_t ldl, bool refine, double* __restrict__ scratch, Acc& acc) {
   acc_zero(acc);
   gemm_nt_mainloop<2>(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);
   if (!refine) {
@@ -351,7 +483,8 @@ __device__ __forceinline__ void tile_solve(GemmStage* stages, double* __restrict
   __syncthreads();
   acc_zero(acc);
   gemm_nt_mainloop<2>(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);  // R Linv^T
-  store_tile_add(T, ldt, scratch, TILE, valid, kb, acc);              // T <- X0 + R Linv^T
+  acc_add_tile(acc, scratch, TILE, valid, kb);                         // + X0 (each thread re-reads its own stores)
+  store_tile<0>(T, ldt, valid, kb, acc, false);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -375,8 +508,9 @@ trsm_tile_kernel(double* __restrict__ T1, int64_t ldt1, int64_t rows1, int64_t s
   T += (int64_t)ti * TILE * ldt;
   const int valid = static_cast<int>(min64(TILE, rows - (int64_t)ti * TILE));
   const bool refine = flag[(int64_t)b * strideW] != 0.0;
+  Acc acc;
   tile_solve(stages, T, ldt, valid, kb, Linv + (int64_t)b * strideW, Lkk + (int64_t)b * strideL, ldl, refine,
-             scratch + (int64_t)b * strideScratch + (int64_t)blockIdx.x * TILE * TILE);
+             scratch + (int64_t)b * strideScratch + (int64_t)blockIdx.x * TILE * TILE, acc);
 }
 
 // --------------------------------------------------------------------------------------
@@ -460,50 +594,58 @@ trsm_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const dou
       __threadfence();
       __syncthreads();
     }
+    Acc xacc;
     tile_solve(stages, Brow + (int64_t)j * TILE, ldb, valid, kb, ws + (int64_t)j * TILE * TILE,
                L + (int64_t)j * TILE * ldl + (int64_t)j * TILE, ldl, flags[j] != 0.0,
-               scratch + (int64_t)ti * TILE * TILE);
+               scratch + (int64_t)ti * TILE * TILE, xacc);
     __threadfence();
     __syncthreads();
   }
 }
 
 // --------------------------------------------------------------------------------------
-// v2: persistent left-looking tile-dataflow Cholesky.  One CTA per SM pulls tile tasks (i, j)
-// from a global ticket counter in column-major order (every dependency of a task has a smaller
-// ticket, so a spinning CTA only ever waits on work that is already running or done: no
-// deadlock, no co-residency requirement).  Task (i, j):
-//     acc = sum_{k<j} L_ik L_jk^T   one long-K DMMA GEMM, waiting per 128-column block on the
-//                                   "ready" flags of the tiles it streams
-//     T   = A_ij - acc              accumulators meet the tile exactly once (HBM traffic n^2 per
-//                                   sweep instead of n^3 / (3 * 128) for the right-looking form)
-//     i == j:  L_jj = chol(T), Linv_jj, refinement flag   (diag_factor_tile)
-//     i >  j:  L_ij = T L_jj^-T                           (tile_solve, after L_jj is ready)
-// Appended row tiles (B) and batched matrices are just more tasks of the same list.
+// v3: persistent left-looking tile-dataflow Cholesky.  One CTA per SM pulls tile tasks from a
+// global ticket counter.  Four kinds of task (tile = 128, k = tile row, j = tile column):
+//   PLAIN (i, j), i >= j + 2 or appended rows:
+//       acc = sum_{l<j} L_il L_jl^T  (one long-K DMMA GEMM that consumes the k-tiles as their
+//       "ready" flags come up), T = A_ij - acc,
+//       then, once L_jj is ready, L_ij = T L_jj^-T.
+//   PRE (k):   A_kk -= sum_{l<k-1} L_kl L_kl^T      (everything of the diagonal update that does
+//              not depend on the previous column), published through pready[k].
+//   HEAD (k):  the whole critical chain of column k-1 -> k in ONE CTA, operands staying on chip:
+//              T = A_{k,k-1} - sum_{l<k-1} ..., wait for L_{k-1,k-1}, X = T L^-T (published as
+//              L_{k,k-1}), X parked in shared memory, S = X X^T (lower) straight out of shared
+//              memory, tile = A_kk(PRE) - S assembled in shared memory, diagonal factor + inverse,
+//              published.  Per column the chain is solve + syrk + factor on one SM with no global
+//              round trip in between (v2: three tasks on three SMs, 125 us per column).
+//   D0:        factor of the first diagonal tile.
+// Ticket order: [D0, HEAD(1)] then for every column g: HEAD(g+2), PLAIN(g+2, g), PRE(g+2),
+// PLAIN(g+3.., g).  Every dependency of a task has a smaller ticket, except that HEAD(g+2) needs
+// the two tickets right behind it; since tickets are handed out in order those are always held
+// by a running CTA (or the next free one), so a spinning CTA only ever waits on running or
+// finished work: deadlock-free for any grid >= 3 without a co-residency requirement.
 // --------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ void wait_ready(const int* flag) {
   while (ld_acquire(flag) == 0) __nanosleep(40);
 }
 
-// gemm_nt_mainloop over K = 128 * ktiles with per-k-tile dependency waits on readyA[kt], readyB[kt].
+// gemm_nt_mainloop over K = 128 * ktiles with per-k-tile dependency waits on readyA[kt], readyB[kt]
+// (every thread acquires the flags before it issues the first chunk of a k-tile).  The copies of
+// chunk c + STAGES - 1 are issued AFTER the DMMAs of chunk c: issued before them they sit in front
+// of the fragment loads in the memory pipe and delay the first DMMAs of every chunk (measured 8 %).
+// (A variant that polled the flags in the background and never blocked while landed chunks
+// remained was measured 4-12 % slower in the throughput-bound regime and no faster in the
+// chain-bound one, so the simple form stays.)
 template <int MODE>
-__device__ __forceinline__ void gemm_nt_mainloop_dep(GemmStage* stages, const double* __restrict__ Ap, int64_t lda,
-                                                     int validA, const double* __restrict__ Bp, int64_t ldb,
-                                                     int validB, int K, Acc& acc, const int* readyA,
-                                                     const int* readyB) {
+__device__ __forceinline__ void gemm_nt_mainloop_dep(GemmStage* stages, const double* __restrict__ Ap,
+                                                              int64_t lda, int validA, const double* __restrict__ Bp,
+                                                              int64_t ldb, int validB, int K, Acc& acc,
+                                                              const int* readyA, const int* readyB) {
   const int warp = canonical_warp(), lane = threadIdx.x & 31;
   const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
   const int nchunks = K / BK;
   const unsigned mask = block_mask<MODE>(wm, wn, validA);
-  constexpr int CPT = TILE / BK;  // chunks per k-tile
+  constexpr int CPT = TILE / BK;
   auto issue = [&](int nc) {
     if (nc % CPT == 0) {
       wait_ready(readyA + nc / CPT);
@@ -528,6 +670,106 @@ __device__ __forceinline__ void gemm_nt_mainloop_dep(GemmStage* stages, const do
   __syncthreads();
 }
 
+// X (accumulator layout) -> shared operand tile Xs[128][DLD].
+__device__ __forceinline__ void acc_to_smem(double* __restrict__ Xs, const Acc& acc) {
+  const int warp = canonical_warp(), lane = threadIdx.x & 31;
+  const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<double2*>(Xs + (acc_row(wm, i) + gid) * DLD + wn * 64 + j * 8 + 2 * tig) =
+          make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
+// acc = lower part of Xs Xs^T (K = 128), both operands straight from the shared tile.  Only the
+// 8 x 32 blocks that touch the lower triangle are computed (static per-warp block lists).
+__device__ __forceinline__ void syrk_from_smem(const double* __restrict__ Xs, Acc& acc) {
+  const int warp = canonical_warp(), lane = threadIdx.x & 31;
+  const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
+  const double* pa = Xs + (wm * 8 + gid) * DLD + tig;
+  const double* pb = Xs + (wn * 64 + gid) * DLD + tig;
+  acc_zero(acc);
+  if (wn == 0) {  // columns 0..63: every row group, except (i = 0, columns 32..63)
+#pragma unroll 2
+    for (int kk = 0; kk < TILE; kk += 4) {
+      double a[4], b[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = pa[i * 32 * DLD + kk];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = pb[j * 8 * DLD + kk];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+#pragma unroll
+      for (int i = 1; i < 4; ++i)
+#pragma unroll
+        for (int j = 4; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  } else {  // columns 64..127: row groups i = 2 (columns 64..95) and i = 3 (all)
+#pragma unroll 2
+    for (int kk = 0; kk < TILE; kk += 4) {
+      double a[2], b[8];
+      a[0] = pa[2 * 32 * DLD + kk];
+      a[1] = pa[3 * 32 * DLD + kk];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = pb[j * 8 * DLD + kk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(acc[2][j][0], acc[2][j][1], a[0], b[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dmma884(acc[3][j][0], acc[3][j][1], a[1], b[j]);
+    }
+  }
+}
+
+// Ls (shared, diagonal-factor layout) = lower(T - acc), zeros above the diagonal, identity
+// padding beyond kb.  T is the diagonal tile in global memory (ld = ldt).
+__device__ __forceinline__ void assemble_diag(double* __restrict__ Ls, const double* __restrict__ T, int64_t ldt,
+                                              int kb, const Acc& acc) {
+  const int warp = canonical_warp(), lane = threadIdx.x & 31;
+  const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
+  const bool vec = ((ldt & 1) == 0) && ((reinterpret_cast<uintptr_t>(T) & 15) == 0);
+#pragma unroll
+  for (int ih = 0; ih < 2; ++ih) {
+    double2 old[2][8];
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii) {
+      const int r = acc_row(wm, 2 * ih + ii) + gid;
+      const double* trow = T + (int64_t)r * ldt;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = wn * 64 + j * 8 + 2 * tig;
+        const bool ok0 = (r < kb) && (c <= r), ok1 = (r < kb) && (c + 1 <= r);
+        old[ii][j] = make_double2(0.0, 0.0);
+        if (ok0 && ok1 && vec) {
+          old[ii][j] = __ldcg(reinterpret_cast<const double2*>(trow + c));
+        } else if (ok0) {
+          old[ii][j].x = __ldcg(trow + c);
+        }
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii) {
+      const int i = 2 * ih + ii;
+      const int r = acc_row(wm, i) + gid;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = wn * 64 + j * 8 + 2 * tig;
+        double v0 = 0.0, v1 = 0.0;
+        if (r < kb) {
+          if (c <= r) v0 = old[ii][j].x - acc[i][j][0];
+          if (c + 1 <= r) v1 = old[ii][j].y - acc[i][j][1];
+        } else {
+          if (c == r) v0 = 1.0;
+          if (c + 1 == r) v1 = 1.0;
+        }
+        *reinterpret_cast<double2*>(Ls + r * DLD + c) = make_double2(v0, v1);
+      }
+    }
+  }
+}
+
 constexpr size_t DF_SMEM_BYTES = DIAG_SMEM_BYTES > GEMM_SMEM_BYTES ? DIAG_SMEM_BYTES : GEMM_SMEM_BYTES;
 constexpr int DF_POOL_TILES = 192;  // scratch tiles for the persistent grid (>= SM count)
 
@@ -539,7 +781,8 @@ struct DfArgs {
   double* pool;                   // gridDim.x scratch tiles
   int32_t* info;
   int* ticket; int* ready;        // ready[(b * (nt + nbt) + i) * nt + j]
-  long long* prof;                // debug: globaltimer stamps of the tasks around column nt/2 (or null)
+  int* pready;                    // pready[b * nt + k]: PRE(k) done
+  long long* prof;                // debug: globaltimer stamps of HEAD(nt/2), HEAD(nt/2 + 1) (or null)
 };
 
 __device__ __forceinline__ long long globaltimer_ns() {
@@ -548,10 +791,21 @@ __device__ __forceinline__ long long globaltimer_ns() {
   return t;
 }
 
+enum { TASK_D0 = 0, TASK_HEAD = 1, TASK_PLAIN = 2, TASK_PRE = 3 };
+
+// Tasks per matrix: prologue and column group g (see the ticket order above).
+__host__ __device__ __forceinline__ int df_prologue_tasks(int nt) { return nt > 1 ? 2 : 1; }
+__host__ __device__ __forceinline__ int df_group_tasks(int nt, int rows_total, int g) {
+  const int first = (g + 1 < nt) ? g + 2 : g + 1;
+  const int nplain = rows_total - first;
+  return (nplain > 0 ? nplain : 0) + ((g + 2 < nt) ? 2 : 0);
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const DfArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_task;
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
+  double* Xs = reinterpret_cast<double*>(smem_raw);  // HEAD: operand tile, then the diagonal-factor tile
   const int tid = threadIdx.x;
   const int rows_total = p.nt + p.nbt;
   double* scratch = p.pool + (int64_t)blockIdx.x * TILE * TILE;
@@ -561,72 +815,113 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
     const int t = s_task;
     __syncthreads();
     if (t >= p.total_tasks) break;
-    // decode ticket -> (column j, matrix b, row tile i); columns outermost, diagonal task first
-    int j = 0, rem = t;
-    for (;; ++j) {
-      const int per_col = p.batch * (rows_total - j);
-      if (rem < per_col) break;
-      rem -= per_col;
+    // ---- decode ticket -> (kind, matrix b, tile row i, tile column j) -----------------------
+    int kind, b, i, j;
+    {
+      const int npro = df_prologue_tasks(p.nt);
+      if (t < p.batch * npro) {
+        b = t / npro;
+        if (t % npro == 0) { kind = TASK_D0; i = 0; j = 0; } else { kind = TASK_HEAD; i = 1; j = 0; }
+      } else {
+        int rem = t - p.batch * npro, g = 0, cnt = 0;
+        for (;; ++g) {
+          cnt = df_group_tasks(p.nt, rows_total, g);
+          if (rem < p.batch * cnt) break;
+          rem -= p.batch * cnt;
+        }
+        b = rem / cnt;
+        const int idx = rem % cnt;
+        j = g;
+        if (g + 2 < p.nt) {
+          if (idx == 0) { kind = TASK_HEAD; i = g + 2; j = g + 1; }
+          else if (idx == 1) { kind = TASK_PLAIN; i = g + 2; }
+          else if (idx == 2) { kind = TASK_PRE; i = g + 2; j = g + 2; }
+          else { kind = TASK_PLAIN; i = g + idx; }
+        } else {
+          kind = TASK_PLAIN;
+          i = ((g + 1 < p.nt) ? g + 2 : g + 1) + idx;
+        }
+      }
     }
-    const int rows_in_col = rows_total - j;
-    const int b = rem / rows_in_col;
-    const int i = j + rem % rows_in_col;
-
     double* Ab = p.A + (int64_t)b * p.strideA;
-    const int kb = static_cast<int>(min64(TILE, p.n - (int64_t)j * TILE));
-    const double* rowj = Ab + (int64_t)j * TILE * p.lda;
-    double* rowi;
-    int64_t ldi;
-    int valid;
-    if (i < p.nt) {
-      rowi = Ab + (int64_t)i * TILE * p.lda; ldi = p.lda;
-      valid = static_cast<int>(min64(TILE, p.n - (int64_t)i * TILE));
-    } else {
-      rowi = p.B + (int64_t)b * p.strideB + (int64_t)(i - p.nt) * TILE * p.ldb; ldi = p.ldb;
-      valid = static_cast<int>(min64(TILE, p.nb - (int64_t)(i - p.nt) * TILE));
-    }
     int* ready_b = p.ready + (int64_t)b * rows_total * p.nt;
-    const int* ready_i = ready_b + (int64_t)i * p.nt;
-    const int* ready_j = ready_b + (int64_t)j * p.nt;
     double* wsb = p.ws + (int64_t)b * p.strideWs;
-    double* T = rowi + (int64_t)j * TILE;
-    // debug stamps: tasks (jp, jp), (jp+1, jp), (jp+1, jp+1) with jp = nt/2
-    long long* pf = nullptr;
-    if (p.prof && b == 0 && tid == 0) {
-      const int jp = p.nt / 2;
-      if (j == jp && i == jp) pf = p.prof;
-      else if (j == jp && i == jp + 1) pf = p.prof + 8;
-      else if (j == jp + 1 && i == jp + 1) pf = p.prof + 16;
-    }
+    double* flags = wsb + (int64_t)p.nt * TILE * TILE;
+    long long* pf = nullptr;  // debug stamps of HEAD(nt/2) and HEAD(nt/2 + 1)
+    if (p.prof && b == 0 && tid == 0 && kind == TASK_HEAD && (i == p.nt / 2 || i == p.nt / 2 + 1))
+      pf = p.prof + 8 * (i - p.nt / 2);
     if (pf) pf[0] = globaltimer_ns();
 
-    if (j > 0) {
+    if (kind == TASK_D0) {
+      const int kb = static_cast<int>(min64(TILE, p.n));
+      diag_load(smem_raw, Ab, p.lda, kb);
+      diag_factor_core(smem_raw, Ab, p.lda, kb, 0, wsb, flags, p.info + b, ready_b, nullptr);
+    } else if (kind == TASK_PRE) {
+      // A_kk -= sum_{l<k-1} L_kl L_kl^T
+      const int k = i;
+      const int kb = static_cast<int>(min64(TILE, p.n - (int64_t)k * TILE));
+      const double* rowk = Ab + (int64_t)k * TILE * p.lda;
       Acc acc;
       acc_zero(acc);
-      // (the masked lower-triangular MODE 1 path is slower than the full tile: its branches break
-      //  the DMMA/LDS software pipeline; measured 2x per chunk)
-      gemm_nt_mainloop_dep<0>(stages, rowi, ldi, valid, rowj, p.lda, kb, j * TILE, acc, ready_i, ready_j);
-      if (pf) pf[1] = globaltimer_ns();
-      store_tile<1>(T, ldi, valid, kb, acc, i == j);
+      gemm_nt_mainloop_dep<0>(stages, rowk, p.lda, kb, rowk, p.lda, kb, (k - 1) * TILE, acc,
+                              ready_b + (int64_t)k * p.nt, ready_b + (int64_t)k * p.nt);
+      store_tile<1>(Ab + (int64_t)k * TILE * p.lda + (int64_t)k * TILE, p.lda, kb, kb, acc, true);
       __threadfence();
       __syncthreads();
-      if (pf) pf[2] = globaltimer_ns();
-    }
-    if (i == j) {
-      diag_factor_tile(smem_raw, T, p.lda, kb, (int64_t)j * TILE, wsb + (int64_t)j * TILE * TILE,
-                       wsb + (int64_t)p.nt * TILE * TILE + j, p.info + b);
+      if (tid == 0) st_release(p.pready + (int64_t)b * p.nt + k, 1);
     } else {
+      // PLAIN (i, j) and HEAD (k = i, j = k - 1) share the accumulate + solve
+      const int kb = static_cast<int>(min64(TILE, p.n - (int64_t)j * TILE));
+      const double* rowj = Ab + (int64_t)j * TILE * p.lda;
+      double* rowi;
+      int64_t ldi;
+      int valid;
+      if (i < p.nt) {
+        rowi = Ab + (int64_t)i * TILE * p.lda; ldi = p.lda;
+        valid = static_cast<int>(min64(TILE, p.n - (int64_t)i * TILE));
+      } else {
+        rowi = p.B + (int64_t)b * p.strideB + (int64_t)(i - p.nt) * TILE * p.ldb; ldi = p.ldb;
+        valid = static_cast<int>(min64(TILE, p.nb - (int64_t)(i - p.nt) * TILE));
+      }
+      const int* ready_i = ready_b + (int64_t)i * p.nt;
+      const int* ready_j = ready_b + (int64_t)j * p.nt;
+      double* T = rowi + (int64_t)j * TILE;
+      Acc acc;
+      if (j > 0) {
+        acc_zero(acc);
+        // (the masked lower-triangular MODE 1 path is slower than the full tile: its branches break
+        //  the DMMA/LDS software pipeline; measured 2x per chunk)
+        gemm_nt_mainloop_dep<0>(stages, rowi, ldi, valid, rowj, p.lda, kb, j * TILE, acc, ready_i, ready_j);
+        store_tile<1>(T, ldi, valid, kb, acc, false);
+        __threadfence();
+        __syncthreads();
+      }
+      if (pf) pf[1] = globaltimer_ns();
       wait_ready(ready_j + j);
-      if (pf) pf[3] = globaltimer_ns();
-      const bool refine = __ldcg(wsb + (int64_t)p.nt * TILE * TILE + j) != 0.0;
+      if (pf) pf[2] = globaltimer_ns();
+      const bool refine = __ldcg(flags + j) != 0.0;
       tile_solve(stages, T, ldi, valid, kb, wsb + (int64_t)j * TILE * TILE, rowj + (int64_t)j * TILE, p.lda, refine,
-                 scratch);
+                 scratch, acc);
+      if (kind == TASK_HEAD) acc_to_smem(Xs, acc);  // the ring is idle: park X as the SYRK operand
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release(ready_b + (int64_t)i * p.nt + j, 1);
+      if (pf) pf[3] = globaltimer_ns();
+      if (kind == TASK_HEAD) {
+        const int k = i;
+        syrk_from_smem(Xs, acc);
+        if (pf) pf[4] = globaltimer_ns();
+        if (k >= 2) wait_ready(p.pready + (int64_t)b * p.nt + k);
+        __syncthreads();  // every warp is done reading Xs
+        double* Tkk = rowi + (int64_t)k * TILE;
+        assemble_diag(Xs, Tkk, p.lda, valid, acc);
+        __syncthreads();
+        if (pf) pf[5] = globaltimer_ns();
+        diag_factor_core(smem_raw, Tkk, p.lda, valid, (int64_t)k * TILE, wsb + (int64_t)k * TILE * TILE, flags + k,
+                         p.info + b, ready_b + (int64_t)k * p.nt + k, nullptr);
+        if (pf) pf[6] = globaltimer_ns();
+      }
     }
-    if (pf) pf[4] = globaltimer_ns();
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) st_release(ready_b + (int64_t)i * p.nt + j, 1);
-    if (pf) pf[5] = globaltimer_ns();
   }
 }
 
@@ -654,7 +949,9 @@ static int64_t ws_scratch_off(int64_t nt) { return nt * TILE * TILE + ((nt + 1) 
 static int64_t ws_stride(int64_t nt, int64_t nbt) { return ws_scratch_off(nt) + (nt + nbt) * TILE * TILE; }
 
 // After the per-matrix regions: [DF_POOL_TILES scratch tiles][int region: ticket (2 ints) + ready flags].
-static int64_t ws_ready_ints(int64_t nt, int64_t nbt, int64_t batch) { return 2 + batch * (nt + nbt) * nt; }
+static int64_t ws_ready_ints(int64_t nt, int64_t nbt, int64_t batch) {
+  return 2 + batch * (nt + nbt) * nt + batch * nt;  // ticket, tile flags, PRE flags
+}
 
 extern "C" size_t gpar_potrf_workspace_bytes(int64_t n, int64_t nb, int64_t batch) {
   if (n <= 0 || batch <= 0) return 0;
@@ -705,8 +1002,9 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
     p.A = A; p.lda = lda; p.n = n; p.strideA = strideA;
     p.B = B; p.ldb = ldb; p.nb = nb; p.strideB = strideB;
     p.batch = (int)batch; p.nt = nt; p.nbt = nbt;
-    int64_t total = 0;
-    for (int j = 0; j < nt; ++j) total += batch * (int64_t)(nt + nbt - j);
+    int64_t total = df_prologue_tasks(nt);
+    for (int g = 0; g < nt; ++g) total += df_group_tasks(nt, nt + nbt, g);
+    total *= batch;
     if (total > 0x7fffffff) { set_error("gpar_potrf: too many tile tasks"); return -9; }
     p.total_tasks = (int)total;
     p.ws = ws; p.strideWs = strideWs;
@@ -715,6 +1013,7 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
     p.prof = g_df_prof;
     int* ints = reinterpret_cast<int*>(p.pool + (int64_t)DF_POOL_TILES * TILE * TILE);
     p.ticket = ints; p.ready = ints + 2;
+    p.pready = p.ready + batch * (int64_t)(nt + nbt) * nt;
     cudaMemsetAsync(ints, 0, sizeof(int) * (size_t)ws_ready_ints(nt, nbt, batch), stream);
     int grid = num_sms < DF_POOL_TILES ? num_sms : DF_POOL_TILES;
     if ((int64_t)grid > total) grid = (int)total;

@@ -18,9 +18,10 @@ for _ in range(2):
 eng.lib.gpar_debug_set_dataflow_prof(None)
 p = prof.cpu().numpy().astype(np.int64)
 t0 = p[0]
-lab = ["task start", "K-loop done", "C stored+fenced", "diag flag seen", "solve/factor done", "flag published"]
-for base, name in ((0, "diag (jp,jp)"), (8, "offdiag (jp+1,jp)"), (16, "diag (jp+1,jp+1)")):
+lab = ["task start", "accumulate done, T stored", "L(k-1,k-1) flag seen", "X solved + published", "X X^T from smem done",
+       "diagonal tile assembled", "factor + inverse published"]
+for base, name in ((0, "HEAD(nt/2)"), (8, "HEAD(nt/2+1)")):
     print(name)
-    for i in range(6):
-        if p[base + i]: print(f"   {lab[i]:20s} t = {(p[base+i]-t0)/1e3:9.2f} us")
-print("diag-to-diag period:", (p[16 + 5] - p[5]) / 1e3, "us")
+    for i in range(7):
+        if p[base + i]: print(f"   {lab[i]:32s} t = {(p[base+i]-t0)/1e3:9.2f} us")
+print("diag-to-diag period:", (p[8 + 6] - p[6]) / 1e3, "us")

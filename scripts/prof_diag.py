@@ -17,19 +17,15 @@ for it in range(3):
     eng.lib.gpar_debug_diag_profile(eng.addr(J), n, n, eng.addr(ws), C.c_void_p(info.data_ptr()), C.c_void_p(prof.data_ptr()), eng.stream)
     torch.cuda.synchronize()
 p = prof.cpu().numpy()
-names = {0: "start", 1: "load", 19: "16-step sweep (L and Linv)", 20: "norms + writeback"}
-for b, k in ((2, 0), (8, 8)):
-    names[b] = f"k={k}: barrier A"; names[b+1] = f"k={k}: row solve (thread 0)"; names[b+2] = f"k={k}: barrier B"
-    names[b+3] = f"k={k}: w0 diag update"; names[b+4] = f"k={k}: w0 factor_block"
-names[13]="  fb(1): after loads"; names[14]="  fb(1): after factor chain"; names[15]="  warp1 k=0 bulk start"; names[16]="  warp1 k=0 bulk end"
-order = sorted([i for i in range(21) if p[i] != 0], key=lambda i: p[i])
+names = {0: "start", 1: "tile loaded", 10: "sweep done", 11: "norms + Linv written, flag", 12: "L written"}
+for q in range(4):
+    names[2 + 2 * q] = f"panel {q}: factor32 + row solves"
+    names[3 + 2 * q] = f"panel {q}: rank-32 update"
+names[13] = "  ||L|| pass"; names[14] = "  Linv pass"
+for q in range(4):
+    names[16 + q] = f"  panel {q}: warp 0 (factor32) done"; names[20 + q] = f"  panel {q}: warp 1 (row solve) done"; names[24 + q] = f"  panel {q}: warp 4 (row solve) done"
+order = sorted([i for i in range(28) if p[i] != 0], key=lambda i: p[i])
 prev = p[0]
 for i in order:
-    print(f"{i:2d} {names.get(i,''):30s} +{p[i]-prev:8d} cyc  (t={p[i]-p[0]})"); prev = p[i]
-sys.exit()
-prev = p[0]
-for i in range(21):
-    if p[i] == 0: continue
-    print(f"{i:2d} {names.get(i,''):22s} +{p[i]-prev:8d} cyc  (t={p[i]-p[0]})")
-    prev = p[i]
-print("total cycles", p[20] - p[0], "=> us @1.965GHz", (p[20] - p[0]) / 1965.0)
+    print(f"{i:2d} {names.get(i,''):34s} +{p[i]-prev:8d} cyc  (t={p[i]-p[0]})"); prev = p[i]
+print("total cycles", p[12] - p[0], "=> us @1.965GHz", (p[12] - p[0]) / 1965.0)
