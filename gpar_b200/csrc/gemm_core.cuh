@@ -1,8 +1,8 @@
 // fp64 tensor-core (DMMA m8n8k4) GEMM core shared by potrf / trsm / syrk:
 //   acc(128x128) += sum_k Arows[r][k] * Brows[c][k]       ("NT": both operands K-contiguous)
-// Operand tiles stream global -> shared through a 4-stage cp.async (LDGSTS, L2-only) ring of
+// Operand tiles stream global -> shared through a 5-stage cp.async (LDGSTS, L2-only) ring of
 // 128 x 16 chunks with a padded row stride of 20 doubles, which makes every 64-bit fragment
-// load bank-conflict free.  8 warps in a 4 (m) x 2 (n) grid, each owning 4 x 8 DMMA tiles (four
+// load bank-conflict free; stage hand-over runs on mbarriers (no CTA-wide barrier per chunk).  8 warps in a 4 (m) x 2 (n) grid, each owning 4 x 8 DMMA tiles (four
 // interleaved 8-row groups x 64 columns), 64 accumulator doubles per thread; 12 shared loads
 // feed 32 DMMAs per k-step of 4.
 //
@@ -13,10 +13,14 @@
 
 namespace gpar {
 
-constexpr int BK = 16;     // k-chunk
-constexpr int LDSM = 20;   // padded shared row stride (doubles): 160 B keeps 16 B alignment
+#ifndef GPAR_BK
+#define GPAR_BK 16
+#endif
+constexpr int BK = GPAR_BK;      // k-chunk
+constexpr int LDSM = BK + 4;     // padded shared row stride (doubles), = 4 (mod 16): conflict-free fragment loads,
+                                 // rows stay 16-byte aligned
 #ifndef GPAR_STAGES
-#define GPAR_STAGES 4
+#define GPAR_STAGES 5
 #endif
 constexpr int STAGES = GPAR_STAGES;
 constexpr int GEMM_THREADS = 256;
@@ -40,10 +44,11 @@ __device__ __forceinline__ void acc_zero(Acc& acc) {
 // columns >= K are zero-filled (src_bytes < 16), so callers never need padded matrices.
 __device__ __forceinline__ void load_chunk(GemmStage& st, const double* __restrict__ Ap, int64_t lda, int validA,
                                            const double* __restrict__ Bp, int64_t ldb, int validB, int k0, int K) {
+  constexpr int SEGS = BK / 2;  // 16-byte segments per row
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int idx = threadIdx.x + it * GEMM_THREADS;  // 0..1023
-    const int r = idx >> 3, seg = idx & 7;
+  for (int it = 0; it < TILE * SEGS / GEMM_THREADS; ++it) {
+    const int idx = threadIdx.x + it * GEMM_THREADS;
+    const int r = idx / SEGS, seg = idx % SEGS;
     const int k = k0 + seg * 2;
     int kb = (K - k) * 8;
     kb = kb < 0 ? 0 : (kb > 16 ? 16 : kb);
@@ -124,34 +129,88 @@ __device__ __forceinline__ void mma_chunk(const GemmStage& st, Acc& acc, int wm,
   }
 }
 
-// Full pipelined mainloop.  All 256 threads must call it.  On return every cp.async has
-// landed and all warps have passed a barrier (the stage ring may be reused immediately).
-template <int MODE = 0>
-__device__ __forceinline__ void gemm_nt_mainloop(GemmStage* stages, const double* __restrict__ Ap, int64_t lda,
-                                                 int validA, const double* __restrict__ Bp, int64_t ldb, int validB,
-                                                 int K, Acc& acc) {
+// ---- mbarrier pipeline: no CTA-wide barrier per chunk ------------------------------------------
+// full[s]  (count 256): armed by cp.async.mbarrier.arrive.noinc of every thread after its copies of
+//                       the chunk; a warp starts the chunk's DMMAs as soon as the phase completes.
+// empty[s] (count 8):   one arrival per warp when it is done reading the stage; a thread refills
+//                       stage (c-1) % S only after that phase, i.e. warps may drift by up to a chunk
+//                       instead of marching in lock step.
+// The barriers live for the whole (persistent) kernel; `n` counts the chunks consumed so far so
+// that stage and phase parity carry over from one mainloop call to the next.
+struct PipeShared {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint32_t n;
+};
+__device__ __forceinline__ PipeShared& pipe_shared() {
+  __shared__ __align__(8) PipeShared ps;
+  return ps;
+}
+__device__ __forceinline__ void pipe_init() {
+  PipeShared& ps = pipe_shared();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&ps.full[s], GEMM_THREADS);
+      mbar_init(&ps.empty[s], GEMM_THREADS / 32);
+    }
+    ps.n = 0;
+    fence_mbar_init();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory");
+}
+
+// WAIT(kt) is called by every thread before it issues the first chunk of k-tile kt.
+template <int MODE, typename WaitFn>
+__device__ __forceinline__ void gemm_nt_pipe(GemmStage* stages, const double* __restrict__ Ap, int64_t lda, int validA,
+                                             const double* __restrict__ Bp, int64_t ldb, int validB, int K, Acc& acc,
+                                             WaitFn wait_tile) {
   const int warp = canonical_warp(), lane = threadIdx.x & 31;
   const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
   const int nchunks = (K + BK - 1) / BK;
   const unsigned mask = block_mask<MODE>(wm, wn, validA);
+  constexpr int CPT = TILE / BK;
+  PipeShared& ps = pipe_shared();
+  const uint32_t base = ps.n;
+  auto issue = [&](int q) {
+    if (q % CPT == 0) wait_tile(q / CPT);
+    const uint32_t g = base + q;
+    load_chunk(stages[g % STAGES], Ap, lda, validA, Bp, ldb, validB, q * BK, K);
+    cp_async_mbar_arrive(&ps.full[g % STAGES]);
+  };
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nchunks) load_chunk(stages[s], Ap, lda, validA, Bp, ldb, validB, s * BK, K);
-    cp_async_commit();
-  }
+  for (int q = 0; q < STAGES - 1; ++q)
+    if (q < nchunks) issue(q);
   for (int c = 0; c < nchunks; ++c) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    mma_chunk<MODE>(stages[c % STAGES], acc, wm, wn, gid, tig, c * BK, mask);
-    // copies after the DMMAs: issued first they queue ahead of the fragment loads (see potrf.cu)
-    const int nc = c + STAGES - 1;
-    if (nc < nchunks) load_chunk(stages[nc % STAGES], Ap, lda, validA, Bp, ldb, validB, nc * BK, K);
-    cp_async_commit();
+    const uint32_t g = base + c;
+    mbar_wait(&ps.full[g % STAGES], (g / STAGES) & 1);
+    mma_chunk<MODE>(stages[g % STAGES], acc, wm, wn, gid, tig, c * BK, mask);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ps.empty[g % STAGES]);
+    const int q = c + STAGES - 1;
+    if (q < nchunks) {
+      if (c >= 1) mbar_wait(&ps.empty[(g - 1) % STAGES], ((g - 1) / STAGES) & 1);
+      issue(q);
+    }
   }
-  cp_async_wait<0>();
+  __syncthreads();  // every warp is done with the ring (callers reuse it), all copies have landed
+  if (threadIdx.x == 0) ps.n = base + nchunks;
   __syncthreads();
 }
 
+template <int MODE = 0>
+__device__ __forceinline__ void gemm_nt_mainloop(GemmStage* stages, const double* __restrict__ Ap, int64_t lda,
+                                                 int validA, const double* __restrict__ Bp, int64_t ldb, int validB,
+                                                 int K, Acc& acc) {
+  gemm_nt_pipe<MODE>(stages, Ap, lda, validA, Bp, ldb, validB, K, acc, [](int) {});
+}
 // Epilogue helpers.  Element (i, j, e) of Acc is C[acc_row(wm, i) + gid][wn*64 + j*8 + 2*tig + e].
 // mode 0: C = acc;  mode 1: C -= acc.  `lower_diag`: only write col <= row (tile on the diagonal).
 template <int MODE>

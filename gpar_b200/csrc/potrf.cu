@@ -36,11 +36,6 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ int ld_relaxed(const int* p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
@@ -495,6 +490,7 @@ trsm_tile_kernel(double* __restrict__ T1, int64_t ldt1, int64_t rows1, int64_t s
                  int64_t strideScratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
+  pipe_init();
   int ti = blockIdx.x;
   const int b = blockIdx.y;
   double* T;
@@ -535,6 +531,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_sub_kernel(const SubArgs
   if (!second && p.lower && tj > ti) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
+  pipe_init();
   const int cols = static_cast<int>(min64(TILE, p.c_cols - (int64_t)tj * TILE));
   const double* Bp = p.Bop + (int64_t)b * p.strideB + (int64_t)tj * TILE * p.ldb;
   const double* Ap;
@@ -579,6 +576,7 @@ trsm_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const dou
                  double* __restrict__ B, int64_t ldb, int64_t nb, double* __restrict__ scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
+  pipe_init();
   const int ti = blockIdx.x;
   double* Brow = B + (int64_t)ti * TILE * ldb;
   const int valid = static_cast<int>(min64(TILE, nb - (int64_t)ti * TILE));
@@ -629,47 +627,21 @@ __device__ __forceinline__ void wait_ready(const int* flag) {
   while (ld_acquire(flag) == 0) __nanosleep(40);
 }
 
-// gemm_nt_mainloop over K = 128 * ktiles with per-k-tile dependency waits on readyA[kt], readyB[kt]
-// (every thread acquires the flags before it issues the first chunk of a k-tile).  The copies of
-// chunk c + STAGES - 1 are issued AFTER the DMMAs of chunk c: issued before them they sit in front
-// of the fragment loads in the memory pipe and delay the first DMMAs of every chunk (measured 8 %).
-// (A variant that polled the flags in the background and never blocked while landed chunks
-// remained was measured 4-12 % slower in the throughput-bound regime and no faster in the
-// chain-bound one, so the simple form stays.)
+// gemm_nt_mainloop over K = 128 * ktiles with per-k-tile dependency waits on readyA[kt], readyB[kt]:
+// every thread acquires the flags before it issues its copies of the first chunk of a k-tile.
+// (Measured alternatives: polling the flags in the background so that landed chunks are never
+// held up by a late flag was 4-12 % slower in the throughput-bound regime and no faster in the
+// chain-bound one; a CTA-wide barrier per chunk instead of the mbarrier ring costs 6 %.)
 template <int MODE>
-__device__ __forceinline__ void gemm_nt_mainloop_dep(GemmStage* stages, const double* __restrict__ Ap,
-                                                              int64_t lda, int validA, const double* __restrict__ Bp,
-                                                              int64_t ldb, int validB, int K, Acc& acc,
-                                                              const int* readyA, const int* readyB) {
-  const int warp = canonical_warp(), lane = threadIdx.x & 31;
-  const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
-  const int nchunks = K / BK;
-  const unsigned mask = block_mask<MODE>(wm, wn, validA);
-  constexpr int CPT = TILE / BK;
-  auto issue = [&](int nc) {
-    if (nc % CPT == 0) {
-      wait_ready(readyA + nc / CPT);
-      if (readyB != readyA) wait_ready(readyB + nc / CPT);
-    }
-    load_chunk(stages[nc % STAGES], Ap, lda, validA, Bp, ldb, validB, nc * BK, K);
-  };
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nchunks) issue(s);
-    cp_async_commit();
-  }
-  for (int c = 0; c < nchunks; ++c) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    mma_chunk<MODE>(stages[c % STAGES], acc, wm, wn, gid, tig, c * BK, mask);
-    const int nc = c + STAGES - 1;
-    if (nc < nchunks) issue(nc);
-    cp_async_commit();
-  }
-  cp_async_wait<0>();
-  __syncthreads();
+__device__ __forceinline__ void gemm_nt_mainloop_dep(GemmStage* stages, const double* __restrict__ Ap, int64_t lda,
+                                                     int validA, const double* __restrict__ Bp, int64_t ldb,
+                                                     int validB, int K, Acc& acc, const int* readyA,
+                                                     const int* readyB) {
+  gemm_nt_pipe<MODE>(stages, Ap, lda, validA, Bp, ldb, validB, K, acc, [&](int kt) {
+    wait_ready(readyA + kt);
+    if (readyB != readyA) wait_ready(readyB + kt);
+  });
 }
-
 // X (accumulator layout) -> shared operand tile Xs[128][DLD].
 __device__ __forceinline__ void acc_to_smem(double* __restrict__ Xs, const Acc& acc) {
   const int warp = canonical_warp(), lane = threadIdx.x & 31;
@@ -809,6 +781,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
   const int tid = threadIdx.x;
   const int rows_total = p.nt + p.nbt;
   double* scratch = p.pool + (int64_t)blockIdx.x * TILE * TILE;
+  pipe_init();
   for (;;) {
     if (tid == 0) s_task = atomicAdd(p.ticket, 1);
     __syncthreads();
