@@ -60,6 +60,13 @@ SIGNATURES = {
     "gpar_potrf_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64]),
     "gpar_trsm_rows_scratch_bytes": (C.c_size_t, [_i64]),
     "gpar_potrf": (_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
+    "gpar_potrf_multi_reset": (_int, [_p, _i64, _i64, _p, _p]),
+    "gpar_potrf_multi": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _int, _int, _p, _p]),
+    "gpar_ipc_alloc": (_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "gpar_ipc_free": (_int, [_p]),
+    "gpar_ipc_export": (_int, [_p, C.c_char_p]),
+    "gpar_ipc_open": (_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "gpar_ipc_close": (_int, [_p]),
     "gpar_trsm_rows": (_int, [_p, _i64, _i64, _p, _p, _i64, _i64, _p, _p]),
     "gpar_syrk_sub": (_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p]),
     "gpar_syrk_add": (_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p]),

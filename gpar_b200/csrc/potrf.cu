@@ -10,6 +10,7 @@
 // sweep: with B = y^T this is the forward solve of the log-marginal; with the joint matrix
 // [[K_aa, .], [K_*a, K_**]] the sweep yields L, V^T = K_*a L^-T and chol(K_** - V^T V) at once.
 #include <cstdlib>
+#include <cstring>
 
 #include "gemm_core.cuh"
 
@@ -38,6 +39,40 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- multi-GPU (one process per GPU): every rank holds a full copy of the matrix and workspace at
+// identical offsets of a peer-mapped allocation; a finished tile is pushed into every peer's copy
+// over NVLink by plain stores at `local address + delta[r]`, followed by a system-scope fence and
+// the peers' ready flags.  world == 1: nothing of this is touched.
+struct Peers {
+  int rank, world;
+  long long delta[GPAR_MAX_PEERS];  // byte distance from this rank's allocation to rank r's (0 for r == rank)
+};
+template <typename T>
+__device__ __forceinline__ T* peer_ptr(T* p, long long d) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + d);
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+// Called by one thread after the CTA's stores were fenced: raise a flag here and on every peer.
+__device__ __forceinline__ void publish_flag(int* flag, const Peers* pe) {
+  if (pe == nullptr || pe->world == 1) {
+    st_release(flag, 1);
+    return;
+  }
+  for (int r = 0; r < pe->world; ++r)
+    if (r != pe->rank) st_release_sys(peer_ptr(flag, pe->delta[r]), 1);
+  st_release_sys(flag, 1);
+}
+__device__ __forceinline__ void fence_publish(const Peers* pe) {
+  if (pe == nullptr || pe->world == 1) __threadfence(); else __threadfence_system();
 }
 
 // Load the lower triangle of a diagonal tile into Ls (zeros above the diagonal, identity padding
@@ -290,7 +325,7 @@ __device__ __forceinline__ void rank32_update(double* __restrict__ Ls, const dou
 __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* __restrict__ Atile, int64_t lda,
                                                  int kb, int64_t j0, double* __restrict__ ws,
                                                  double* __restrict__ flag_out, int32_t* __restrict__ info_b,
-                                                 int* ready_flag, long long* prof) {
+                                                 int* ready_flag, const Peers* pe, long long* prof) {
 #define GPAR_PROF(i) do { if (prof && threadIdx.x == 0) prof[i] = clock64(); } while (0)
   double* Ls = reinterpret_cast<double*>(smem_raw);
   double* rdiag = Ls + TILE * DLD;
@@ -299,6 +334,7 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
   int* s_int = reinterpret_cast<int*>(red + 32);  // [0] first bad pivot, [1] refine
   const int tid = threadIdx.x, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
   const int warp = canonical_warp();
+  const bool multi = (pe != nullptr) && (pe->world > 1);
   if (tid == 0) s_int[0] = 0;
   GPAR_PROF(1);
 #pragma unroll 1
@@ -369,6 +405,14 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
         double* dst = ws + r * TILE + c;
         *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
         *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
+        if (multi) {
+          for (int pr = 0; pr < pe->world; ++pr) {
+            if (pr == pe->rank) continue;
+            double* pd = peer_ptr(dst, pe->delta[pr]);
+            *reinterpret_cast<double2*>(pd) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(pd + 2) = make_double2(v[2], v[3]);
+          }
+        }
         const double s = (fabs(v[0]) + fabs(v[1])) + (fabs(v[2]) + fabs(v[3]));
         if (rb == 0) isum[0] += s; else if (rb == 1) isum[1] += s; else if (rb == 2) isum[2] += s; else isum[3] += s;
       }
@@ -395,13 +439,17 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
     const double kappa = mL * mI;
     const int refine = (kappa > REFINE_KAPPA || !(kappa == kappa)) ? 1 : 0;
     *flag_out = refine ? 1.0 : 0.0;
+    if (multi)
+      for (int pr = 0; pr < pe->world; ++pr)
+        if (pr != pe->rank) *peer_ptr(flag_out, pe->delta[pr]) = refine ? 1.0 : 0.0;
     s_int[1] = refine;
     if (s_int[0] != 0 && *info_b == 0) *info_b = static_cast<int32_t>(j0) + s_int[0];
   }
-  __threadfence();
+  if (!multi) __threadfence();
   __syncthreads();
   const bool refine = s_int[1] != 0;
-  if (ready_flag && !refine && tid == 0) st_release(ready_flag, 1);
+  const bool early = ready_flag && !refine && !multi;  // multi-GPU: one publication after L went out
+  if (early && tid == 0) st_release(ready_flag, 1);
   GPAR_PROF(11);
   // ---- L (row major).  Only the lower triangle is stored, plus zeros in the strictly upper part of
   // each 32 x 32 diagonal block: every consumer (MODE 2 GEMMs skip whole 32-column halves per
@@ -419,20 +467,23 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
       for (int q = 0; q < 4; ++q)
         if (c + q > r) v[q] = 0.0;
       double* dst = Atile + (int64_t)r * lda + c;
-      if (vec_ok && c + 3 < kb) {
-        *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
-        *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
-      } else {
+      for (int pr = 0; pr < (multi ? pe->world : 1); ++pr) {
+        double* pd = multi ? peer_ptr(dst, pe->delta[pr]) : dst;  // delta[rank] == 0: the local copy
+        if (vec_ok && c + 3 < kb) {
+          *reinterpret_cast<double2*>(pd) = make_double2(v[0], v[1]);
+          *reinterpret_cast<double2*>(pd + 2) = make_double2(v[2], v[3]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (c + q < kb) dst[q] = v[q];
+          for (int q = 0; q < 4; ++q)
+            if (c + q < kb) pd[q] = v[q];
+        }
       }
     }
   }
-  if (ready_flag && refine) {
-    __threadfence();
+  if (ready_flag && !early) {
+    fence_publish(pe);
     __syncthreads();
-    if (tid == 0) st_release(ready_flag, 1);
+    if (tid == 0) publish_flag(ready_flag, pe);
   }
   GPAR_PROF(12);
 #undef GPAR_PROF
@@ -450,7 +501,7 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, 
   if (prof && threadIdx.x == 0) prof[0] = clock64();
   diag_load(smem_raw, Atile, lda, kb);
   diag_factor_core(smem_raw, Atile, lda, kb, j0, wsb + (int64_t)kt * TILE * TILE,
-                   wsb + (int64_t)nt_total * TILE * TILE + kt, info + b, nullptr, prof);
+                   wsb + (int64_t)nt_total * TILE * TILE + kt, info + b, nullptr, nullptr, prof);
 }
 
 // --------------------------------------------------------------------------------------
@@ -623,8 +674,12 @@ trsm_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const dou
 // by a running CTA (or the next free one), so a spinning CTA only ever waits on running or
 // finished work: deadlock-free for any grid >= 3 without a co-residency requirement.
 // --------------------------------------------------------------------------------------
-__device__ __forceinline__ void wait_ready(const int* flag) {
-  while (ld_acquire(flag) == 0) __nanosleep(40);
+__device__ __forceinline__ void wait_ready(const int* flag, bool sys = false) {
+  if (sys) {
+    while (ld_acquire_sys(flag) == 0) __nanosleep(40);  // the flag (and its tile) may have come from a peer GPU
+  } else {
+    while (ld_acquire(flag) == 0) __nanosleep(40);
+  }
 }
 
 // gemm_nt_mainloop over K = 128 * ktiles with per-k-tile dependency waits on readyA[kt], readyB[kt]:
@@ -636,10 +691,10 @@ template <int MODE>
 __device__ __forceinline__ void gemm_nt_mainloop_dep(GemmStage* stages, const double* __restrict__ Ap, int64_t lda,
                                                      int validA, const double* __restrict__ Bp, int64_t ldb,
                                                      int validB, int K, Acc& acc, const int* readyA,
-                                                     const int* readyB) {
+                                                     const int* readyB, bool sys) {
   gemm_nt_pipe<MODE>(stages, Ap, lda, validA, Bp, ldb, validB, K, acc, [&](int kt) {
-    wait_ready(readyA + kt);
-    if (readyB != readyA) wait_ready(readyB + kt);
+    wait_ready(readyA + kt, sys);
+    if (readyB != readyA) wait_ready(readyB + kt, sys);
   });
 }
 // X (accumulator layout) -> shared operand tile Xs[128][DLD].
@@ -755,6 +810,7 @@ struct DfArgs {
   int* ticket; int* ready;        // ready[(b * (nt + nbt) + i) * nt + j]
   int* pready;                    // pready[b * nt + k]: PRE(k) done
   long long* prof;                // debug: globaltimer stamps of HEAD(nt/2), HEAD(nt/2 + 1) (or null)
+  Peers peers;                    // multi-GPU: rank, world and the peers' address deltas (world == 1: unused)
 };
 
 __device__ __forceinline__ long long globaltimer_ns() {
@@ -776,9 +832,13 @@ __host__ __device__ __forceinline__ int df_group_tasks(int nt, int rows_total, i
 __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const DfArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_task;
+  __shared__ Peers s_peers;
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
   double* Xs = reinterpret_cast<double*>(smem_raw);  // HEAD: operand tile, then the diagonal-factor tile
   const int tid = threadIdx.x;
+  if (tid == 0) s_peers = p.peers;
+  const bool multi = p.peers.world > 1;
+  const Peers* pe = multi ? &s_peers : nullptr;
   const int rows_total = p.nt + p.nbt;
   double* scratch = p.pool + (int64_t)blockIdx.x * TILE * TILE;
   pipe_init();
@@ -816,6 +876,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
         }
       }
     }
+    // multi-GPU: tile rows are dealt round-robin; a rank only runs the tasks of its own rows
+    if (multi && ((kind == TASK_D0) ? 0 : (i % p.peers.world)) != p.peers.rank) continue;
     double* Ab = p.A + (int64_t)b * p.strideA;
     int* ready_b = p.ready + (int64_t)b * rows_total * p.nt;
     double* wsb = p.ws + (int64_t)b * p.strideWs;
@@ -828,7 +890,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
     if (kind == TASK_D0) {
       const int kb = static_cast<int>(min64(TILE, p.n));
       diag_load(smem_raw, Ab, p.lda, kb);
-      diag_factor_core(smem_raw, Ab, p.lda, kb, 0, wsb, flags, p.info + b, ready_b, nullptr);
+      diag_factor_core(smem_raw, Ab, p.lda, kb, 0, wsb, flags, p.info + b, ready_b, pe, nullptr);
     } else if (kind == TASK_PRE) {
       // A_kk -= sum_{l<k-1} L_kl L_kl^T
       const int k = i;
@@ -837,7 +899,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
       Acc acc;
       acc_zero(acc);
       gemm_nt_mainloop_dep<0>(stages, rowk, p.lda, kb, rowk, p.lda, kb, (k - 1) * TILE, acc,
-                              ready_b + (int64_t)k * p.nt, ready_b + (int64_t)k * p.nt);
+                              ready_b + (int64_t)k * p.nt, ready_b + (int64_t)k * p.nt, multi);
       store_tile<1>(Ab + (int64_t)k * TILE * p.lda + (int64_t)k * TILE, p.lda, kb, kb, acc, true);
       __threadfence();
       __syncthreads();
@@ -864,21 +926,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
         acc_zero(acc);
         // (the masked lower-triangular MODE 1 path is slower than the full tile: its branches break
         //  the DMMA/LDS software pipeline; measured 2x per chunk)
-        gemm_nt_mainloop_dep<0>(stages, rowi, ldi, valid, rowj, p.lda, kb, j * TILE, acc, ready_i, ready_j);
+        gemm_nt_mainloop_dep<0>(stages, rowi, ldi, valid, rowj, p.lda, kb, j * TILE, acc, ready_i, ready_j, multi);
         store_tile<1>(T, ldi, valid, kb, acc, false);
         __threadfence();
         __syncthreads();
       }
       if (pf) pf[1] = globaltimer_ns();
-      wait_ready(ready_j + j);
+      wait_ready(ready_j + j, multi);
       if (pf) pf[2] = globaltimer_ns();
       const bool refine = __ldcg(flags + j) != 0.0;
       tile_solve(stages, T, ldi, valid, kb, wsb + (int64_t)j * TILE * TILE, rowj + (int64_t)j * TILE, p.lda, refine,
                  scratch, acc);
+      if (multi)  // L_ij into every peer's copy of the matrix (NVLink stores straight from the accumulators)
+        for (int pr = 0; pr < p.peers.world; ++pr)
+          if (pr != p.peers.rank) store_tile<0>(peer_ptr(T, p.peers.delta[pr]), ldi, valid, kb, acc, false);
       if (kind == TASK_HEAD) acc_to_smem(Xs, acc);  // the ring is idle: park X as the SYRK operand
-      __threadfence();
+      fence_publish(pe);
       __syncthreads();
-      if (tid == 0) st_release(ready_b + (int64_t)i * p.nt + j, 1);
+      if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe);
       if (pf) pf[3] = globaltimer_ns();
       if (kind == TASK_HEAD) {
         const int k = i;
@@ -891,7 +956,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
         __syncthreads();
         if (pf) pf[5] = globaltimer_ns();
         diag_factor_core(smem_raw, Tkk, p.lda, valid, (int64_t)k * TILE, wsb + (int64_t)k * TILE * TILE, flags + k,
-                         p.info + b, ready_b + (int64_t)k * p.nt + k, nullptr);
+                         p.info + b, ready_b + (int64_t)k * p.nt + k, pe, nullptr);
         if (pf) pf[6] = globaltimer_ns();
       }
     }
@@ -941,6 +1006,52 @@ extern "C" size_t gpar_trsm_rows_scratch_bytes(int64_t nb) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Launch of the persistent dataflow kernel (single GPU: peers.world == 1).  reset != 0 zeroes the
+// ticket / ready flags first (the multi-GPU driver does that in a separate call, followed by a
+// barrier over the ranks, because peers write flags into this workspace).
+static int df_reset(double* ws, int64_t n, int64_t nb, int64_t batch, cudaStream_t stream) {
+  const int64_t nt = (n + TILE - 1) / TILE, nbt = nb > 0 ? (nb + TILE - 1) / TILE : 0;
+  double* pool = ws + batch * ws_stride(nt, nbt);
+  int* ints = reinterpret_cast<int*>(pool + (int64_t)DF_POOL_TILES * TILE * TILE);
+  cudaMemsetAsync(ints, 0, sizeof(int) * (size_t)ws_ready_ints(nt, nbt, batch), stream);
+  return 0;
+}
+
+static int launch_dataflow(double* A, int64_t lda, int64_t n, int64_t strideA, double* B, int64_t ldb, int64_t nb,
+                           int64_t strideB, int64_t batch, double* ws, int32_t* info, const Peers& peers, bool reset,
+                           cudaStream_t stream) {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int nt = (int)((n + TILE - 1) / TILE);
+  const int nbt = nb > 0 ? (int)((nb + TILE - 1) / TILE) : 0;
+  DfArgs p;
+  p.A = A; p.lda = lda; p.n = n; p.strideA = strideA;
+  p.B = B; p.ldb = ldb; p.nb = nb; p.strideB = strideB;
+  p.batch = (int)batch; p.nt = nt; p.nbt = nbt;
+  int64_t total = df_prologue_tasks(nt);
+  for (int g = 0; g < nt; ++g) total += df_group_tasks(nt, nt + nbt, g);
+  total *= batch;
+  if (total > 0x7fffffff) { set_error("gpar_potrf: too many tile tasks"); return -9; }
+  p.total_tasks = (int)total;
+  p.ws = ws; p.strideWs = ws_stride(nt, nbt);
+  p.pool = ws + batch * p.strideWs;
+  p.info = info;
+  p.prof = g_df_prof;
+  p.peers = peers;
+  int* ints = reinterpret_cast<int*>(p.pool + (int64_t)DF_POOL_TILES * TILE * TILE);
+  p.ticket = ints; p.ready = ints + 2;
+  p.pready = p.ready + batch * (int64_t)(nt + nbt) * nt;
+  if (reset) df_reset(ws, n, nb, batch, stream);
+  int grid = num_sms < DF_POOL_TILES ? num_sms : DF_POOL_TILES;
+  if ((int64_t)grid > total) grid = (int)total;
+  potrf_dataflow_kernel<<<grid, GEMM_THREADS, DF_SMEM_BYTES, stream>>>(p);
+  return check_launch("gpar_potrf");
+}
+
 extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, double* B, int64_t ldb, int64_t nb,
                           int64_t strideB, int64_t batch, double* ws, int32_t* info, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -965,33 +1076,10 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
   double* scratch = ws + ws_scratch_off(nt);
   static const bool use_v1 = (getenv("GPAR_POTRF_V1") != nullptr);
   if (!use_v1) {
-    static int num_sms = 0;
-    if (num_sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    DfArgs p;
-    p.A = A; p.lda = lda; p.n = n; p.strideA = strideA;
-    p.B = B; p.ldb = ldb; p.nb = nb; p.strideB = strideB;
-    p.batch = (int)batch; p.nt = nt; p.nbt = nbt;
-    int64_t total = df_prologue_tasks(nt);
-    for (int g = 0; g < nt; ++g) total += df_group_tasks(nt, nt + nbt, g);
-    total *= batch;
-    if (total > 0x7fffffff) { set_error("gpar_potrf: too many tile tasks"); return -9; }
-    p.total_tasks = (int)total;
-    p.ws = ws; p.strideWs = strideWs;
-    p.pool = ws + batch * strideWs;
-    p.info = info;
-    p.prof = g_df_prof;
-    int* ints = reinterpret_cast<int*>(p.pool + (int64_t)DF_POOL_TILES * TILE * TILE);
-    p.ticket = ints; p.ready = ints + 2;
-    p.pready = p.ready + batch * (int64_t)(nt + nbt) * nt;
-    cudaMemsetAsync(ints, 0, sizeof(int) * (size_t)ws_ready_ints(nt, nbt, batch), stream);
-    int grid = num_sms < DF_POOL_TILES ? num_sms : DF_POOL_TILES;
-    if ((int64_t)grid > total) grid = (int)total;
-    potrf_dataflow_kernel<<<grid, GEMM_THREADS, DF_SMEM_BYTES, stream>>>(p);
-    return check_launch("gpar_potrf");
+    Peers solo;
+    solo.rank = 0; solo.world = 1;
+    for (int r = 0; r < GPAR_MAX_PEERS; ++r) solo.delta[r] = 0;
+    return launch_dataflow(A, lda, n, strideA, B, ldb, nb, strideB, batch, ws, info, solo, true, stream);
   }
   for (int k = 0; k < nt; ++k) {
     const int64_t j0 = (int64_t)k * TILE;
@@ -1022,6 +1110,63 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
   }
   return check_launch("gpar_potrf");
 }
+
+// ---- multi-GPU Cholesky: one process per GPU, tile rows dealt round-robin ---------
+extern "C" int gpar_potrf_multi_reset(double* ws, int64_t n, int64_t nb, int32_t* info, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!ws || !aligned16(ws)) { set_error("gpar_potrf_multi_reset: bad workspace"); return -1; }
+  if (!info) return -4;
+  cudaMemsetAsync(info, 0, sizeof(int32_t), stream);
+  if (n <= 0) return 0;
+  df_reset(ws, n, nb, 1, stream);
+  return check_launch("gpar_potrf_multi_reset");
+}
+
+extern "C" int gpar_potrf_multi(double* A, int64_t lda, int64_t n, double* B, int64_t ldb, int64_t nb, double* ws,
+                                int32_t* info, int rank, int world, const int64_t* peer_delta_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!A || !aligned16(A)) { set_error("gpar_potrf_multi: A null or not 16-byte aligned"); return -1; }
+  if (lda < n || (lda & 1)) { set_error("gpar_potrf_multi: lda must be even and >= n"); return -2; }
+  if (n < 0) return -3;
+  if (nb > 0 && (!B || !aligned16(B) || ldb < n || (ldb & 1))) { set_error("gpar_potrf_multi: bad appended rows"); return -4; }
+  if (!ws || !aligned16(ws)) { set_error("gpar_potrf_multi: bad workspace"); return -7; }
+  if (!info) return -8;
+  if (world < 1 || world > GPAR_MAX_PEERS || rank < 0 || rank >= world) { set_error("gpar_potrf_multi: bad rank/world"); return -9; }
+  if (world > 1 && !peer_delta_bytes) return -11;
+  set_smem_attrs();
+  if (n == 0) return 0;
+  Peers pe;
+  pe.rank = rank; pe.world = world;
+  for (int r = 0; r < GPAR_MAX_PEERS; ++r) pe.delta[r] = (r < world && r != rank) ? (long long)peer_delta_bytes[r] : 0;
+  for (int r = 0; r < world; ++r)
+    if (pe.delta[r] & 15) { set_error("gpar_potrf_multi: peer deltas must be multiples of 16 bytes"); return -11; }
+  return launch_dataflow(A, lda, n, 0, B, ldb, nb, 0, 1, ws, info, pe, false, stream);
+}
+
+// Peer-mappable device memory (CUDA IPC): every rank allocates the same size, exports its handle,
+// and opens its peers' handles; `gpar_potrf_multi` is handed the address differences.
+extern "C" int gpar_ipc_alloc(size_t bytes, void** ptr) {
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) { set_error("gpar_ipc_alloc: %s", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+  return 0;
+}
+extern "C" int gpar_ipc_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? 0 : -1; }
+extern "C" int gpar_ipc_export(void* ptr, unsigned char* handle64) {
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) { set_error("gpar_ipc_export: %s", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+extern "C" int gpar_ipc_open(const unsigned char* handle64, void** ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { set_error("gpar_ipc_open: %s", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+  return 0;
+}
+extern "C" int gpar_ipc_close(void* ptr) { return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? 0 : -1; }
 
 extern "C" int gpar_trsm_rows(const double* L, int64_t ldl, int64_t n, const double* ws, double* B, int64_t ldb,
                               int64_t nb, double* scratch, void* stream_) {

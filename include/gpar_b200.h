@@ -32,6 +32,7 @@ extern "C" {
 #define GPAR_TILE 128        /* Cholesky tile edge; workspace is sized in tiles */
 #define GPAR_MAX_TERMS 8
 #define GPAR_MAX_FEATS 96
+#define GPAR_MAX_PEERS 8       /* ranks of one NVLink domain that gpar_potrf_multi spans */
 
 /* Kernel terms after lowering to a feature map (see gpar_kernel_spec_t). */
 enum { GPAR_TERM_EQ = 0, GPAR_TERM_RQ = 1, GPAR_TERM_LINEAR = 2, GPAR_TERM_CONST = 3 };
@@ -100,6 +101,29 @@ int gpar_gram_batched(const gpar_kernel_spec_t* spec, const double* X, int64_t l
 size_t gpar_potrf_workspace_bytes(int64_t n, int64_t nb, int64_t batch);
 int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, double* B, int64_t ldb, int64_t nb,
                int64_t strideB, int64_t batch, double* ws, int32_t* info, void* stream);
+
+/* K2, multi-GPU (BASELINE config 5): the same factorisation spread over `world` GPUs of one
+ * NVLink domain, one process per GPU.  Every rank holds a full-size copy of A (n x n, lower: all ranks build the
+ * same Gram matrix), of B and of the workspace, at IDENTICAL offsets inside one peer-mapped allocation
+ * (gpar_ipc_* below, or any other means of mapping peer memory); peer_delta_bytes[r] is the address of rank r's
+ * allocation minus the address of this rank's (ignored for r == rank).  Tile rows are dealt round-robin:
+ * rank r factors / solves the tiles of rows r, r + world, ... and pushes every finished tile, the inverses
+ * of the diagonal tiles and the ready flags into all peers' copies by plain NVLink stores from inside the
+ * kernel, so operand streaming stays local and the transfer overlaps the math tile by tile.  On return (after
+ * the caller has synchronised the stream AND passed a barrier over the ranks) every rank holds the complete
+ * L, B L^-T and workspace.  Protocol:  gpar_potrf_multi_reset on every rank -> stream sync + barrier over the
+ * ranks -> gpar_potrf_multi on every rank -> stream sync + barrier.  info: as gpar_potrf, set on the rank that
+ * owns the offending diagonal tile (reduce with max over ranks). */
+int gpar_potrf_multi_reset(double* ws, int64_t n, int64_t nb, int32_t* info, void* stream);
+int gpar_potrf_multi(double* A, int64_t lda, int64_t n, double* B, int64_t ldb, int64_t nb, double* ws,
+                     int32_t* info, int rank, int world, const int64_t* peer_delta_bytes, void* stream);
+
+/* Peer-mappable device memory over CUDA IPC: allocate, export a 64-byte handle, open a peer's handle. */
+int gpar_ipc_alloc(size_t bytes, void** ptr);
+int gpar_ipc_free(void* ptr);
+int gpar_ipc_export(void* ptr, unsigned char* handle64);
+int gpar_ipc_open(const unsigned char* handle64, void** ptr);
+int gpar_ipc_close(void* ptr);
 
 /* K4 -- B (nb x n) <- B L^-T given L and the `ws` of its gpar_potrf.  This is
  * (L^-1 K(x_a, x_))^T of PosteriorMean / PosteriorKernel. */

@@ -50,3 +50,112 @@ def test_sharded_chains_nccl_world2():
         assert p.exitcode == 0
     err_smp, err_mean = q.get()
     assert err_smp <= 1e-12 and err_mean <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# Sharded Cholesky (gpar_potrf_multi): world 1 through the same entry point on any GPU box,
+# world 2 over CUDA IPC / NVLink when two GPUs are visible.
+# ---------------------------------------------------------------------------------------------
+def _sharded_case(eng, n, nb, group, seed=0):
+    """Factor the same SPD matrix with gpar_potrf (one GPU) and potrf_sharded; return the max abs
+    differences of L, B L^-T and the inverse tiles."""
+    import scipy.linalg as sla
+
+    from gpar_b200.dist import PeerBuffer, potrf_layout, potrf_sharded
+    from gpar_b200.spec import lower_terms
+
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0, 1, (n, 2))
+    d = rng.uniform(0.05, 0.2, n)
+    Bh = rng.standard_normal((max(nb, 1), n))
+    spec = lower_terms([dict(type="eq", variance=1.0, cols=[0, 1], scales=[0.25, 0.25])])
+    Xd, dd = eng.to_device(X).reshape(-1), eng.to_device(d)
+    lay = potrf_layout(eng, n, nb)
+    ld = lay["ld"]
+    Bp = np.zeros((max(nb, 1), ld)); Bp[:, :n] = Bh
+    # single-GPU reference through gpar_potrf
+    J1 = eng.empty(n * ld); B1 = eng.to_device(Bp).reshape(-1)
+    eng.gram(spec, Xd, 2, n, J1, ld, diag=dd, lower_only=True)
+    ws1, info1 = eng.potrf(J1, ld, n, B=B1 if nb else None, ldb=ld, nb=nb)
+    # sharded
+    buf = PeerBuffer(eng, lay["bytes"], group)
+    J2 = buf.view(lay["a"], n * ld)
+    eng.gram(spec, Xd, 2, n, J2, ld, diag=dd, lower_only=True)
+    if nb:
+        buf.view(lay["b"], nb * ld).copy_(eng.to_device(Bp).reshape(-1)[: nb * ld])
+    potrf_sharded(eng, buf, n, nb, group)
+    L1 = np.tril(J1.cpu().numpy().reshape(n, ld)[:, :n])
+    L2 = np.tril(J2.cpu().numpy().reshape(n, ld)[:, :n])
+    K = np.exp(-0.5 * ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1) / 0.25 ** 2) + np.diag(d + 1e-12)
+    Lref = sla.cholesky(K, lower=True)
+    err_ref = np.linalg.norm(L2 - Lref) / np.linalg.norm(Lref)
+    dL = float(np.abs(L1 - L2).max())
+    dB = 0.0
+    if nb:
+        dB = float(np.abs(B1.cpu().numpy()[: nb * ld] - buf.view(lay["b"], nb * ld).cpu().numpy()).max())
+    nt = (n + 127) // 128
+    W1 = ws1.cpu().numpy()[: nt * 128 * 128]
+    W2 = buf.view(lay["ws"], nt * 128 * 128).cpu().numpy()
+    dW = float(np.abs(np.tril(W1.reshape(nt, 128, 128)) - np.tril(W2.reshape(nt, 128, 128))).max())
+    buf.close()
+    return dL, dB, dW, float(err_ref)
+
+
+@pytest.mark.parametrize("n,nb", [(100, 1), (640, 0), (1000, 130)])
+def test_potrf_sharded_world1_equals_potrf(n, nb):
+    from gpar_b200.engine import Engine
+
+    eng = Engine()
+    dL, dB, dW, err_ref = _sharded_case(eng, n, nb, None)
+    assert dL == 0.0 and dB == 0.0 and dW == 0.0  # same kernel, same tile arithmetic
+    assert err_ref <= 1e-12 * (1 + np.log(n))
+
+
+def _worker_potrf(rank, world, port, q):
+    import torch.distributed as dist
+
+    from gpar_b200.dist import layer_logpdf_sharded
+    from gpar_b200.engine import Engine
+    from gpar_b200.spec import lower_terms
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    eng = Engine()
+    res = [_sharded_case(eng, n, nb, None if world == 1 else dist.group.WORLD, seed=n) for n, nb in
+           ((300, 1), (1500, 0), (2100, 200))]
+    # the sharded dense log-marginal of one layer against scipy
+    rng = np.random.default_rng(5)
+    n = 1800
+    X = rng.uniform(0, 1, (n, 2)); d = np.full(n, 0.1); y = rng.standard_normal(n)
+    spec = lower_terms([dict(type="eq", variance=1.0, cols=[0, 1], scales=[0.25, 0.25])])
+    lp = layer_logpdf_sharded(eng, spec, eng.to_device(X), eng.to_device(d), eng.to_device(y), dist.group.WORLD)
+    if rank == 0:
+        import scipy.linalg as sla
+
+        K = np.exp(-0.5 * ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1) / 0.25 ** 2) + np.diag(d + 1e-12)
+        Lr = sla.cholesky(K, lower=True)
+        u = sla.solve_triangular(Lr, y, lower=True)
+        ref = -0.5 * (2 * np.log(np.diag(Lr)).sum() + n * np.log(2 * np.pi) + u @ u)
+        q.put((res, float(abs(lp - ref) / abs(ref))))
+    dist.destroy_process_group()
+
+
+def test_potrf_sharded_world2_nvlink():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker_potrf, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    res, rel_lp = q.get()
+    for dL, dB, dW, err_ref in res:
+        assert dL == 0.0 and dB == 0.0 and dW == 0.0  # tile arithmetic does not depend on the owner
+        assert err_ref <= 1e-11
+    assert rel_lp <= 1e-10
