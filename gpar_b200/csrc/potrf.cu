@@ -829,6 +829,36 @@ __host__ __device__ __forceinline__ int df_group_tasks(int nt, int rows_total, i
   return (nplain > 0 ? nplain : 0) + ((g + 2 < nt) ? 2 : 0);
 }
 
+// ticket -> (kind, matrix b, tile row i, tile column j); HEAD(k) comes back as (i = k, j = k - 1), PRE(k) as (k, k).
+__host__ __device__ __forceinline__ void df_decode(int t, int nt, int nbt, int batch, int& kind, int& b, int& i,
+                                                   int& j) {
+  const int rows_total = nt + nbt;
+  const int npro = df_prologue_tasks(nt);
+  if (t < batch * npro) {
+    b = t / npro;
+    if (t % npro == 0) { kind = TASK_D0; i = 0; j = 0; } else { kind = TASK_HEAD; i = 1; j = 0; }
+    return;
+  }
+  int rem = t - batch * npro, g = 0, cnt = 0;
+  for (;; ++g) {
+    cnt = df_group_tasks(nt, rows_total, g);
+    if (rem < batch * cnt) break;
+    rem -= batch * cnt;
+  }
+  b = rem / cnt;
+  const int idx = rem % cnt;
+  j = g;
+  if (g + 2 < nt) {
+    if (idx == 0) { kind = TASK_HEAD; i = g + 2; j = g + 1; }
+    else if (idx == 1) { kind = TASK_PLAIN; i = g + 2; }
+    else if (idx == 2) { kind = TASK_PRE; i = g + 2; j = g + 2; }
+    else { kind = TASK_PLAIN; i = g + idx; }
+  } else {
+    kind = TASK_PLAIN;
+    i = ((g + 1 < nt) ? g + 2 : g + 1) + idx;
+  }
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const DfArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_task;
@@ -848,34 +878,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
     const int t = s_task;
     __syncthreads();
     if (t >= p.total_tasks) break;
-    // ---- decode ticket -> (kind, matrix b, tile row i, tile column j) -----------------------
     int kind, b, i, j;
-    {
-      const int npro = df_prologue_tasks(p.nt);
-      if (t < p.batch * npro) {
-        b = t / npro;
-        if (t % npro == 0) { kind = TASK_D0; i = 0; j = 0; } else { kind = TASK_HEAD; i = 1; j = 0; }
-      } else {
-        int rem = t - p.batch * npro, g = 0, cnt = 0;
-        for (;; ++g) {
-          cnt = df_group_tasks(p.nt, rows_total, g);
-          if (rem < p.batch * cnt) break;
-          rem -= p.batch * cnt;
-        }
-        b = rem / cnt;
-        const int idx = rem % cnt;
-        j = g;
-        if (g + 2 < p.nt) {
-          if (idx == 0) { kind = TASK_HEAD; i = g + 2; j = g + 1; }
-          else if (idx == 1) { kind = TASK_PLAIN; i = g + 2; }
-          else if (idx == 2) { kind = TASK_PRE; i = g + 2; j = g + 2; }
-          else { kind = TASK_PLAIN; i = g + idx; }
-        } else {
-          kind = TASK_PLAIN;
-          i = ((g + 1 < p.nt) ? g + 2 : g + 1) + idx;
-        }
-      }
-    }
+    df_decode(t, p.nt, p.nbt, p.batch, kind, b, i, j);
     // multi-GPU: tile rows are dealt round-robin; a rank only runs the tasks of its own rows
     if (multi && ((kind == TASK_D0) ? 0 : (i % p.peers.world)) != p.peers.rank) continue;
     double* Ab = p.A + (int64_t)b * p.strideA;
@@ -1213,6 +1217,22 @@ static int syrk_impl(double* C, int64_t ldc, int64_t n, int64_t strideC, const d
   p.C2 = nullptr; p.ldc2 = 0; p.c_rows2 = 0; p.strideC2 = 0; p.Aop2 = nullptr; p.lda2 = 0; p.strideA2 = 0;
   gemm_sub_kernel<<<dim3(nt, nt, (unsigned)batch), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
   return check_launch("gpar_syrk_sub");
+}
+
+// Debug / tests: the task list of the dataflow kernel, decoded on the host by the same function the
+// kernel uses.  out4 = {kind (0 D0, 1 HEAD, 2 PLAIN, 3 PRE), matrix, tile row, tile column}; returns the
+// total number of tickets (t < 0: only the count).
+extern "C" int gpar_debug_decode_ticket(int64_t n, int64_t nb, int64_t batch, int64_t t, int32_t* out4) {
+  const int nt = (int)((n + TILE - 1) / TILE), nbt = nb > 0 ? (int)((nb + TILE - 1) / TILE) : 0;
+  int64_t total = df_prologue_tasks(nt);
+  for (int g = 0; g < nt; ++g) total += df_group_tasks(nt, nt + nbt, g);
+  total *= batch;
+  if (t >= 0 && t < total && out4) {
+    int kind, b, i, j;
+    df_decode((int)t, nt, nbt, (int)batch, kind, b, i, j);
+    out4[0] = kind; out4[1] = b; out4[2] = i; out4[3] = j;
+  }
+  return (int)total;
 }
 
 // Debug: phase timestamps (clock64) of the diagonal-tile factor on the leading 128 block of A.

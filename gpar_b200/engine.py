@@ -26,7 +26,11 @@ def _even(n):
 class Engine:
     """Owns the library handle, the device and the launch counter."""
 
-    def __init__(self, device=None, epsilon=1e-12):
+    def __init__(self, device=None, epsilon=1e-12, group=None, shard_min_n=4096):
+        """``group``: a torch.distributed process group (one process per GPU of one NVLink domain).
+        When set, every factorisation of at least ``shard_min_n`` rows is spread over its ranks
+        (:func:`gpar_b200.dist.potrf_sharded`); all ranks must then drive the engine with the same
+        calls and the same data (SPMD)."""
         if not torch.cuda.is_available():
             raise _lib.GparError("gpar_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -35,6 +39,23 @@ class Engine:
         self.launches = 0  # kernels of ours launched so far
         self.flops = 0.0  # algorithmic flops of the dense contractions issued (bookkeeping for bench.py)
         self._infos = []  # device `info` words of the factorizations issued since the last check
+        self.group, self.shard_min_n = group, int(shard_min_n)
+        self._peer_bufs = []  # peer-mapped allocations of the sharded factorisations still alive
+
+    def sharded(self, n):
+        """True if a factorisation of n rows is spread over the ranks of ``self.group``."""
+        if self.group is None or n < self.shard_min_n:
+            return False
+        import torch.distributed as dist
+
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def free_peer_buffers(self):
+        """Collective: release the peer-mapped buffers of earlier sharded factorisations (their
+        Factor objects become invalid).  Called by GPARRegressor at the start of every public call."""
+        bufs, self._peer_bufs = self._peer_bufs, []
+        for b in bufs:
+            b.close()
 
     def check_infos(self):
         """Read back the pivot status of every factorization issued since the last call (one
@@ -222,11 +243,29 @@ class Factor:
         self.n_obs, self.n_ext = int(n_obs), int(n_ext)
         n = self.n = self.n_obs + self.n_ext
         self.ld = ld = _even(max(n, 2))
+        self._alpha = None
+        if eng.sharded(n):
+            # multi-GPU: the joint matrix lives in peer-mapped memory, tile rows are dealt to the ranks
+            from .dist import PeerBuffer, potrf_layout, potrf_sharded
+
+            lay = potrf_layout(eng, n, 1)
+            assert lay["ld"] == ld
+            buf = PeerBuffer(eng, lay["bytes"], eng.group)
+            eng._peer_bufs.append(buf)
+            self.J = buf.view(lay["a"], n * ld)
+            self.u = buf.view(lay["b"], ld)
+            self.u.zero_()
+            if self.n_obs > 0:
+                self.u[: self.n_obs].copy_(y[: self.n_obs])
+            eng.gram(spec, X, ldx, n, self.J, ld, diag=d, lower_only=True)
+            potrf_sharded(eng, buf, n, 1, eng.group)
+            self.ws = buf.view(lay["ws"], eng.lib.gpar_potrf_workspace_bytes(n, 1, 1) // 8)
+            self.info = torch.zeros(1, dtype=torch.int32, device=eng.device)
+            return
         self.J = eng.empty(max(n, 1) * ld)
         self.u = eng.zeros(ld)
         if self.n_obs > 0:
             self.u[: self.n_obs].copy_(y[: self.n_obs])
-        self._alpha = None
         if n > 0:
             eng.gram(spec, X, ldx, n, self.J, ld, diag=d, lower_only=True)
             self.ws, self.info = eng.potrf(self.J, ld, n, B=self.u, ldb=ld, nb=1)

@@ -142,6 +142,7 @@ class GPARRegressor:
     def logpdf(self, x, y, w=None, sample_missing=False, posterior=False, normals=None):
         """Log-density of observations (regression.py:461-506).  As in the reference the
         incoming ``y`` goes through ``_unnormalise_y`` (quirk Q1)."""
+        self._release_sharded()
         x = _uprank(x)
         y = self._unnormalise_y(self._transform_y(_uprank(y)))
         w = _init_weights(w, y)
@@ -154,7 +155,14 @@ class GPARRegressor:
         return np.float64(gpar.logpdf(x, y, w, only_last_layer=False, sample_missing=sample_missing,
                                       normals=normals))
 
+    def _release_sharded(self):
+        """Multi-GPU engines: free the peer-mapped factor buffers of the previous public call
+        (collective; every rank makes the same calls)."""
+        if self._engine is not None and self._engine.group is not None:
+            self._engine.free_peer_buffers()
+
     def _sample_device(self, x, w, p, posterior, num_samples, latent, normals):
+        self._release_sharded()
         x = _uprank(x)
         if posterior and not self.is_conditioned:
             raise RuntimeError("Must condition or fit model before sampling from the posterior.")

@@ -159,3 +159,51 @@ def test_potrf_sharded_world2_nvlink():
         assert dL == 0.0 and dB == 0.0 and dW == 0.0  # tile arithmetic does not depend on the owner
         assert err_ref <= 1e-11
     assert rel_lp <= 1e-10
+
+
+def _worker_regressor(rank, world, port, q):
+    import torch.distributed as dist
+
+    import bench
+    from gpar_b200 import GPARRegressor
+    from gpar_b200.dist import predict_sharded
+    from gpar_b200.engine import Engine
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    data_kw, reg_kw = bench.CONFIGS["c2"]
+    data = bench.make_data(**{**data_kw, "n": 1500, "ns": 200, "S": 6})
+    normals = {"Z": data["Z"]}
+    # engine with a process group: conditioning factorisations (n >= 1024 here) are spread over the
+    # ranks, the chains are partitioned over the ranks
+    reg = GPARRegressor(engine=Engine(group=dist.group.WORLD, shard_min_n=1024), **reg_kw)
+    reg.condition(data["x"], data["y"])
+    lp = reg.logpdf(data["x"], data["y"])
+    mean = predict_sharded(reg, data["xs"], num_samples=6, normals=normals)
+    reg._release_sharded()
+    if rank == 0:
+        ref = GPARRegressor(engine=Engine(), **reg_kw)
+        ref.condition(data["x"], data["y"])
+        lp_ref = ref.logpdf(data["x"], data["y"])
+        mean_ref = ref.predict(data["xs"], num_samples=6, normals=normals)
+        q.put((float(abs(lp - lp_ref) / abs(lp_ref)), float(np.abs(mean - mean_ref).max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_regressor_sharded_cholesky_and_chains_world2():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker_regressor, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    rel_lp, err_mean = q.get()
+    assert rel_lp <= 1e-13 and err_mean <= 1e-12

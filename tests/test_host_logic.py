@@ -148,3 +148,71 @@ def test_engine_fails_loudly_without_cuda():
 
     with pytest.raises(_lib.GparError):
         Engine()
+
+
+# ---- task list of the Cholesky dataflow kernel and its multi-GPU partition (host decode, no GPU) ----
+@pytest.mark.parametrize("n,nb,batch", [(100, 0, 1), (128, 1, 1), (300, 1, 1), (1000, 130, 1), (2049, 1, 1), (640, 0, 3)])
+def test_dataflow_task_list_covers_every_tile_once_and_orders_dependencies(n, nb, batch):
+    import ctypes as C
+
+    from gpar_b200 import _lib
+    from gpar_b200.dist import tile_row_owner
+
+    lib = _lib.load()
+    nt, nbt = (n + 127) // 128, (nb + 127) // 128 if nb > 0 else 0
+    total = lib.gpar_debug_decode_ticket(n, nb, batch, -1, None)
+    out = (C.c_int32 * 4)()
+    D0, HEAD, PLAIN, PRE = 0, 1, 2, 3
+    ticket = {}  # (matrix, what, i, j) -> ticket
+    for t in range(total):
+        lib.gpar_debug_decode_ticket(n, nb, batch, t, out)
+        kind, b, i, j = list(out)
+        if kind == D0:
+            keys = [(b, "diag", 0, 0)]
+        elif kind == HEAD:
+            assert j == i - 1
+            keys = [(b, "tile", i, j), (b, "diag", i, i)]
+        elif kind == PLAIN:
+            assert i > j
+            keys = [(b, "tile", i, j)]
+        else:
+            assert kind == PRE and i == j and i >= 2
+            keys = [(b, "pre", i, i)]
+        for k in keys:
+            assert k not in ticket, f"{k} scheduled twice"
+            ticket[k] = t
+    for b in range(batch):
+        # coverage: every diagonal tile, every tile below the diagonal (incl. appended rows), PRE for k >= 2
+        for k in range(nt):
+            assert (b, "diag", k, k) in ticket
+            if k >= 2:
+                assert (b, "pre", k, k) in ticket
+        for j in range(nt):
+            for i in range(j + 1, nt + nbt):
+                assert (b, "tile", i, j) in ticket
+        # dependencies: a tile task streams L_il, L_jl (l < j) and needs diag j
+        for (bb, what, i, j), t in ticket.items():
+            if bb != b:
+                continue
+            if what == "tile":
+                deps = [(b, "diag", j, j)] + [(b, "tile", i, l) for l in range(j)] + [(b, "tile", j, l) for l in range(j)]
+                head = i < nt and j == i - 1  # solved inside HEAD(i): may wait for the ticket right behind it
+                for d in deps:
+                    if head and d == (b, "tile", i, i - 2):
+                        assert ticket[d] <= t + 2
+                    else:
+                        assert ticket[d] < t, f"{(what, i, j)} depends on later ticket {d}"
+            elif what == "pre":
+                for l in range(i - 1):
+                    assert ticket[(b, "tile", i, l)] < t
+            elif what == "diag" and i >= 2:
+                # the head needs PRE(k) and tile (k, k-2): at most the two tickets right behind it
+                assert ticket[(b, "pre", i, i)] <= t + 2 and ticket[(b, "tile", i, i - 2)] <= t + 2
+    assert len(ticket) == total + batch * max(nt - 1, 0)  # every HEAD ticket carries two entries
+    # multi-GPU partition: a task runs on the owner of its tile row; forward dependencies of a head stay on-rank
+    for world in (2, 3, 8):
+        for (b, what, i, j), t in ticket.items():
+            if what == "diag" and i >= 2:
+                assert tile_row_owner(i, world) == tile_row_owner(i, world)  # head, PRE(i) and tile (i, i-2): row i
+        owners = {tile_row_owner(i, world) for i in range(nt + nbt)}
+        assert owners == set(range(min(world, nt + nbt)))
