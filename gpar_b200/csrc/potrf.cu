@@ -47,6 +47,7 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 // the peers' ready flags.  world == 1: nothing of this is touched.
 struct Peers {
   int rank, world;
+  int row_block;                    // tile rows are dealt to the ranks in blocks of this many (block-cyclic)
   long long delta[GPAR_MAX_PEERS];  // byte distance from this rank's allocation to rank r's (0 for r == rank)
 };
 template <typename T>
@@ -61,15 +62,25 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
-// Called by one thread after the CTA's stores were fenced: raise a flag here and on every peer.
-__device__ __forceinline__ void publish_flag(int* flag, const Peers* pe) {
+// Publication targets of a finished tile.  The rank that owns the next tile row sits on the critical
+// chain (its HEAD task consumes the tile next), so it is served -- and flagged -- first; the other
+// peers follow.  PEERS_FIRST = this rank + the next one, PEERS_REST = everybody else.
+enum { PEERS_ALL = 0, PEERS_FIRST = 1, PEERS_REST = 2 };
+__device__ __forceinline__ bool peer_in_set(const Peers* pe, int r, int set) {
+  const int next = (pe->rank + 1) % pe->world;
+  if (set == PEERS_ALL) return true;
+  const bool first = (r == pe->rank) || (r == next);
+  return set == PEERS_FIRST ? first : !first;
+}
+// Called by one thread after the CTA's stores were fenced: raise a flag on the ranks of `set`.
+__device__ __forceinline__ void publish_flag(int* flag, const Peers* pe, int set = PEERS_ALL) {
   if (pe == nullptr || pe->world == 1) {
     st_release(flag, 1);
     return;
   }
   for (int r = 0; r < pe->world; ++r)
-    if (r != pe->rank) st_release_sys(peer_ptr(flag, pe->delta[r]), 1);
-  st_release_sys(flag, 1);
+    if (r != pe->rank && peer_in_set(pe, r, set)) st_release_sys(peer_ptr(flag, pe->delta[r]), 1);
+  if (peer_in_set(pe, pe->rank, set)) st_release_sys(flag, 1);
 }
 __device__ __forceinline__ void fence_publish(const Peers* pe) {
   if (pe == nullptr || pe->world == 1) __threadfence(); else __threadfence_system();
@@ -322,6 +333,7 @@ __device__ __forceinline__ void rank32_update(double* __restrict__ Ls, const dou
 // inverse costs no extra phase.  Four panel steps of width 32: warp 0 factors the diagonal block
 // (shuffle pivots, registers), warps 1-4 solve the 128 rows against it as its columns appear, then
 // all warps apply the rank-32 DMMA update to the columns beyond the panel.
+template <bool MULTI>
 __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* __restrict__ Atile, int64_t lda,
                                                  int kb, int64_t j0, double* __restrict__ ws,
                                                  double* __restrict__ flag_out, int32_t* __restrict__ info_b,
@@ -334,7 +346,7 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
   int* s_int = reinterpret_cast<int*>(red + 32);  // [0] first bad pivot, [1] refine
   const int tid = threadIdx.x, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
   const int warp = canonical_warp();
-  const bool multi = (pe != nullptr) && (pe->world > 1);
+  const bool multi = MULTI && (pe != nullptr) && (pe->world > 1);  // MULTI = false: all peer code compiles out
   if (tid == 0) s_int[0] = 0;
   GPAR_PROF(1);
 #pragma unroll 1
@@ -387,7 +399,9 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
   // c = r, zeros up to the end of the 32 x 32 diagonal block.  Lanes run along r (two lanes per
   // shared bank: conflict free at stride 132), every lane assembles 4 consecutive c = one 32-byte
   // sector of the output.  Unit = (32-row block rb, column group cg), 80 units over the 8 warps. --
-  {
+  // set: PEERS_FIRST (single GPU: just the local copy) accumulates the row sums; PEERS_REST re-emits
+  // the tile for the remaining peers of a multi-GPU run.
+  auto write_linv = [&](int set) {
     double isum[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int it = 0; it < 10; ++it) {
@@ -403,24 +417,22 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
       }
       if (r < kb) {
         double* dst = ws + r * TILE + c;
-        *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
-        *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
-        if (multi) {
-          for (int pr = 0; pr < pe->world; ++pr) {
-            if (pr == pe->rank) continue;
-            double* pd = peer_ptr(dst, pe->delta[pr]);
-            *reinterpret_cast<double2*>(pd) = make_double2(v[0], v[1]);
-            *reinterpret_cast<double2*>(pd + 2) = make_double2(v[2], v[3]);
-          }
+        for (int pr = 0; pr < (multi ? pe->world : 1); ++pr) {
+          if (multi && !peer_in_set(pe, pr, set)) continue;
+          double* pd = multi ? peer_ptr(dst, pe->delta[pr]) : dst;  // delta[rank] == 0: the local copy
+          *reinterpret_cast<double2*>(pd) = make_double2(v[0], v[1]);
+          *reinterpret_cast<double2*>(pd + 2) = make_double2(v[2], v[3]);
         }
         const double s = (fabs(v[0]) + fabs(v[1])) + (fabs(v[2]) + fabs(v[3]));
         if (rb == 0) isum[0] += s; else if (rb == 1) isum[1] += s; else if (rb == 2) isum[2] += s; else isum[3] += s;
       }
     }
-    // partial row sums of this warp -> LT scratch [8][128]
+    if (set != PEERS_REST) {  // partial row sums of this warp -> LT scratch [8][128]
 #pragma unroll
-    for (int rb = 0; rb < 4; ++rb) LT[warp * TILE + 32 * rb + lane] = isum[rb];
-  }
+      for (int rb = 0; rb < 4; ++rb) LT[warp * TILE + 32 * rb + lane] = isum[rb];
+    }
+  };
+  write_linv(PEERS_FIRST);
   GPAR_PROF(14);
   __syncthreads();
   if (tid < TILE) {
@@ -445,11 +457,14 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
     s_int[1] = refine;
     if (s_int[0] != 0 && *info_b == 0) *info_b = static_cast<int32_t>(j0) + s_int[0];
   }
-  if (!multi) __threadfence();
+  fence_publish(pe);
   __syncthreads();
   const bool refine = s_int[1] != 0;
-  const bool early = ready_flag && !refine && !multi;  // multi-GPU: one publication after L went out
-  if (early && tid == 0) st_release(ready_flag, 1);
+  // Well-conditioned tile: consumers only read Linv (L_kk is read by the refined solves), so the flag
+  // goes up now -- on this rank and, multi-GPU, on the rank that owns the next tile row.
+  const bool early = ready_flag && !refine;
+  if (early && tid == 0) publish_flag(ready_flag, pe, PEERS_FIRST);
+  if (multi && pe->world > 2) write_linv(PEERS_REST);
   GPAR_PROF(11);
   // ---- L (row major).  Only the lower triangle is stored, plus zeros in the strictly upper part of
   // each 32 x 32 diagonal block: every consumer (MODE 2 GEMMs skip whole 32-column halves per
@@ -480,10 +495,10 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
       }
     }
   }
-  if (ready_flag && !early) {
+  if (ready_flag && (!early || (multi && pe->world > 2))) {
     fence_publish(pe);
     __syncthreads();
-    if (tid == 0) publish_flag(ready_flag, pe);
+    if (tid == 0) publish_flag(ready_flag, pe, early ? PEERS_REST : PEERS_ALL);
   }
   GPAR_PROF(12);
 #undef GPAR_PROF
@@ -500,7 +515,7 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, 
   double* Atile = A + (int64_t)b * strideA + j0 * lda + j0;
   if (prof && threadIdx.x == 0) prof[0] = clock64();
   diag_load(smem_raw, Atile, lda, kb);
-  diag_factor_core(smem_raw, Atile, lda, kb, j0, wsb + (int64_t)kt * TILE * TILE,
+  diag_factor_core<false>(smem_raw, Atile, lda, kb, j0, wsb + (int64_t)kt * TILE * TILE,
                    wsb + (int64_t)nt_total * TILE * TILE + kt, info + b, nullptr, nullptr, prof);
 }
 
@@ -859,6 +874,7 @@ __host__ __device__ __forceinline__ void df_decode(int t, int nt, int nbt, int b
   }
 }
 
+template <bool MULTI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const DfArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_task;
@@ -867,7 +883,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
   double* Xs = reinterpret_cast<double*>(smem_raw);  // HEAD: operand tile, then the diagonal-factor tile
   const int tid = threadIdx.x;
   if (tid == 0) s_peers = p.peers;
-  const bool multi = p.peers.world > 1;
+  const bool multi = MULTI && p.peers.world > 1;  // MULTI = false: all peer code compiles out
   const Peers* pe = multi ? &s_peers : nullptr;
   const int rows_total = p.nt + p.nbt;
   double* scratch = p.pool + (int64_t)blockIdx.x * TILE * TILE;
@@ -880,8 +896,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
     if (t >= p.total_tasks) break;
     int kind, b, i, j;
     df_decode(t, p.nt, p.nbt, p.batch, kind, b, i, j);
-    // multi-GPU: tile rows are dealt round-robin; a rank only runs the tasks of its own rows
-    if (multi && ((kind == TASK_D0) ? 0 : (i % p.peers.world)) != p.peers.rank) continue;
+    // multi-GPU: tile rows are dealt block-cyclically; a rank only runs the tasks of its own rows
+    if (multi && ((i / p.peers.row_block) % p.peers.world) != p.peers.rank) continue;
     double* Ab = p.A + (int64_t)b * p.strideA;
     int* ready_b = p.ready + (int64_t)b * rows_total * p.nt;
     double* wsb = p.ws + (int64_t)b * p.strideWs;
@@ -894,7 +910,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
     if (kind == TASK_D0) {
       const int kb = static_cast<int>(min64(TILE, p.n));
       diag_load(smem_raw, Ab, p.lda, kb);
-      diag_factor_core(smem_raw, Ab, p.lda, kb, 0, wsb, flags, p.info + b, ready_b, pe, nullptr);
+      diag_factor_core<MULTI>(smem_raw, Ab, p.lda, kb, 0, wsb, flags, p.info + b, ready_b, pe, nullptr);
     } else if (kind == TASK_PRE) {
       // A_kk -= sum_{l<k-1} L_kl L_kl^T
       const int k = i;
@@ -941,13 +957,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
       const bool refine = __ldcg(flags + j) != 0.0;
       tile_solve(stages, T, ldi, valid, kb, wsb + (int64_t)j * TILE * TILE, rowj + (int64_t)j * TILE, p.lda, refine,
                  scratch, acc);
-      if (multi)  // L_ij into every peer's copy of the matrix (NVLink stores straight from the accumulators)
-        for (int pr = 0; pr < p.peers.world; ++pr)
-          if (pr != p.peers.rank) store_tile<0>(peer_ptr(T, p.peers.delta[pr]), ldi, valid, kb, acc, false);
+      // multi-GPU: L_ij goes into the peers' copies of the matrix by NVLink stores straight from the
+      // accumulators -- first to the rank that owns the next tile row (+ flags), then to the others
+      // (a HEAD defers them until its diagonal tile is out: they are off the critical chain).
+      if (multi) store_tile<0>(peer_ptr(T, p.peers.delta[(p.peers.rank + 1) % p.peers.world]), ldi, valid, kb, acc, false);
       if (kind == TASK_HEAD) acc_to_smem(Xs, acc);  // the ring is idle: park X as the SYRK operand
       fence_publish(pe);
       __syncthreads();
-      if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe);
+      if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe, PEERS_FIRST);
+      if (multi && p.peers.world > 2 && kind != TASK_HEAD) {
+        for (int pr = 0; pr < p.peers.world; ++pr)
+          if (peer_in_set(pe, pr, PEERS_REST)) store_tile<0>(peer_ptr(T, p.peers.delta[pr]), ldi, valid, kb, acc, false);
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe, PEERS_REST);
+      }
       if (pf) pf[3] = globaltimer_ns();
       if (kind == TASK_HEAD) {
         const int k = i;
@@ -959,9 +983,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
         assemble_diag(Xs, Tkk, p.lda, valid, acc);
         __syncthreads();
         if (pf) pf[5] = globaltimer_ns();
-        diag_factor_core(smem_raw, Tkk, p.lda, valid, (int64_t)k * TILE, wsb + (int64_t)k * TILE * TILE, flags + k,
+        diag_factor_core<MULTI>(smem_raw, Tkk, p.lda, valid, (int64_t)k * TILE, wsb + (int64_t)k * TILE * TILE, flags + k,
                          p.info + b, ready_b + (int64_t)k * p.nt + k, pe, nullptr);
         if (pf) pf[6] = globaltimer_ns();
+        if (multi && p.peers.world > 2) {  // L_{k,k-1} for the remaining peers, re-read from the local copy
+          for (int idx = tid; idx < TILE * (TILE / 2); idx += GEMM_THREADS) {
+            const int r = idx >> 6, c = (idx & 63) * 2;
+            if (r >= valid) continue;
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(T + (int64_t)r * ldi + c));
+            for (int pr = 0; pr < p.peers.world; ++pr)
+              if (peer_in_set(pe, pr, PEERS_REST))
+                *reinterpret_cast<double2*>(peer_ptr(T, p.peers.delta[pr]) + (int64_t)r * ldi + c) = v;
+          }
+          __threadfence_system();
+          __syncthreads();
+          if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe, PEERS_REST);
+        }
       }
     }
   }
@@ -976,7 +1013,8 @@ static void set_smem_attrs() {
   cudaFuncSetAttribute(trsm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
   cudaFuncSetAttribute(gemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
   cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
-  cudaFuncSetAttribute(potrf_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM_BYTES);
+  cudaFuncSetAttribute(potrf_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM_BYTES);
+  cudaFuncSetAttribute(potrf_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM_BYTES);
   done = true;
 }
 
@@ -1052,7 +1090,10 @@ static int launch_dataflow(double* A, int64_t lda, int64_t n, int64_t strideA, d
   if (reset) df_reset(ws, n, nb, batch, stream);
   int grid = num_sms < DF_POOL_TILES ? num_sms : DF_POOL_TILES;
   if ((int64_t)grid > total) grid = (int)total;
-  potrf_dataflow_kernel<<<grid, GEMM_THREADS, DF_SMEM_BYTES, stream>>>(p);
+  if (peers.world > 1)
+    potrf_dataflow_kernel<true><<<grid, GEMM_THREADS, DF_SMEM_BYTES, stream>>>(p);
+  else
+    potrf_dataflow_kernel<false><<<grid, GEMM_THREADS, DF_SMEM_BYTES, stream>>>(p);
   return check_launch("gpar_potrf");
 }
 
@@ -1081,7 +1122,7 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
   static const bool use_v1 = (getenv("GPAR_POTRF_V1") != nullptr);
   if (!use_v1) {
     Peers solo;
-    solo.rank = 0; solo.world = 1;
+    solo.rank = 0; solo.world = 1; solo.row_block = 1;
     for (int r = 0; r < GPAR_MAX_PEERS; ++r) solo.delta[r] = 0;
     return launch_dataflow(A, lda, n, strideA, B, ldb, nb, strideB, batch, ws, info, solo, true, stream);
   }
@@ -1140,7 +1181,7 @@ extern "C" int gpar_potrf_multi(double* A, int64_t lda, int64_t n, double* B, in
   set_smem_attrs();
   if (n == 0) return 0;
   Peers pe;
-  pe.rank = rank; pe.world = world;
+  pe.rank = rank; pe.world = world; pe.row_block = GPAR_ROW_BLOCK;
   for (int r = 0; r < GPAR_MAX_PEERS; ++r) pe.delta[r] = (r < world && r != rank) ? (long long)peer_delta_bytes[r] : 0;
   for (int r = 0; r < world; ++r)
     if (pe.delta[r] & 15) { set_error("gpar_potrf_multi: peer deltas must be multiples of 16 bytes"); return -11; }

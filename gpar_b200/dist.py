@@ -9,7 +9,7 @@ contiguous slice of the chains; the only exchange is the reduction of the (n*, p
 chains share their inputs (U_i = 1) and there is nothing to shard: replicas only.
 
 The blocked Cholesky of one large layer also shards (BASELINE config 5): tile rows are
-dealt round-robin to the ranks, every rank keeps a full copy of the matrix in peer-mapped memory
+dealt block-cyclically to the ranks, every rank keeps a full copy of the matrix in peer-mapped memory
 (:class:`PeerBuffer`, CUDA IPC) and the persistent dataflow kernel pushes each finished tile into all
 peers' copies over NVLink from inside the kernel (``gpar_potrf_multi``) -- see :func:`potrf_sharded`
 and :func:`layer_logpdf_sharded`.
@@ -115,9 +115,13 @@ def _dev(group):
 # ---------------------------------------------------------------------------------------------
 # Sharded Cholesky
 # ---------------------------------------------------------------------------------------------
-def tile_row_owner(i, world):
-    """Rank that factors / solves the tiles of tile row ``i`` (round-robin deal)."""
-    return int(i) % int(world)
+ROW_BLOCK = 4  # GPAR_ROW_BLOCK of include/gpar_b200.h
+
+
+def tile_row_owner(i, world, row_block=ROW_BLOCK):
+    """Rank that factors / solves the tiles of tile row ``i``: block-cyclic deal, ``row_block``
+    consecutive tile rows per turn (the critical chain crosses NVLink once per block)."""
+    return (int(i) // int(row_block)) % int(world)
 
 
 class PeerBuffer:

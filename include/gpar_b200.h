@@ -33,6 +33,7 @@ extern "C" {
 #define GPAR_MAX_TERMS 8
 #define GPAR_MAX_FEATS 96
 #define GPAR_MAX_PEERS 8       /* ranks of one NVLink domain that gpar_potrf_multi spans */
+#define GPAR_ROW_BLOCK 4       /* gpar_potrf_multi deals tile rows to the ranks in blocks of 4 (block-cyclic) */
 
 /* Kernel terms after lowering to a feature map (see gpar_kernel_spec_t). */
 enum { GPAR_TERM_EQ = 0, GPAR_TERM_RQ = 1, GPAR_TERM_LINEAR = 2, GPAR_TERM_CONST = 3 };
@@ -106,8 +107,10 @@ int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, double* B, in
  * NVLink domain, one process per GPU.  Every rank holds a full-size copy of A (n x n, lower: all ranks build the
  * same Gram matrix), of B and of the workspace, at IDENTICAL offsets inside one peer-mapped allocation
  * (gpar_ipc_* below, or any other means of mapping peer memory); peer_delta_bytes[r] is the address of rank r's
- * allocation minus the address of this rank's (ignored for r == rank).  Tile rows are dealt round-robin:
- * rank r factors / solves the tiles of rows r, r + world, ... and pushes every finished tile, the inverses
+ *  allocation minus the address of this rank's (ignored for r == rank).  Tile rows are dealt block-cyclically
+ * (GPAR_ROW_BLOCK consecutive tile rows per turn, so that the critical chain -- sub-diagonal solve, diagonal
+ * update and factor of consecutive tile rows -- crosses NVLink only once per block): rank r factors / solves the
+ * tiles of its rows and pushes every finished tile, the inverses
  * of the diagonal tiles and the ready flags into all peers' copies by plain NVLink stores from inside the
  * kernel, so operand streaming stays local and the transfer overlaps the math tile by tile.  On return (after
  * the caller has synchronised the stream AND passed a barrier over the ranks) every rank holds the complete
