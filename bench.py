@@ -369,6 +369,12 @@ def measure_fp64_peaks(eng):
     return out
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at this shape, from the
+# committed `ncu --set full` capture (profiles/r1_ncu_summary.md): 4.455 GB read + 0.278 GB written.
+NCU_DRAM_BYTES_PER_LAUNCH = 4.455251e9 + 0.277513e9
+NCU_DRAM_SOURCE = "ncu --set full capture of potrf_dataflow_kernel at n=8424 (profiles/r1_ncu_summary.md), per launch"
+
+
 def measure_dominant_kernel(eng, peaks):
     """Roofline of the dominant kernel, potrf_dataflow_kernel (persistent tile-dataflow Cholesky,
     fp64 DMMA): one launch factors the joint [training; test] matrix of a C3 layer (n = 8424 rows,
@@ -402,7 +408,7 @@ def measure_dominant_kernel(eng, peaks):
     alg_bytes = 2 * 8.0 * n * (n + 1) / 2
     return {"kernel": "potrf_dataflow_kernel (persistent tile-dataflow Cholesky, DMMA m8n8k4)", "bound": "tensor",
             "achieved": ach, "peak": peaks["dgemm_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["dgemm_tflops"],
-            "traffic": None, "launch_ms": avg * 1e3, "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes,
+            "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_DRAM_SOURCE, "launch_ms": avg * 1e3, "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes,
             "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (MEASURED_PEAKS.json has no fp64 entry)",
             "shape": {"n": n, "appended_rows": 1}}
 
