@@ -684,10 +684,12 @@ trsm_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const dou
 //              round trip in between (v2: three tasks on three SMs, 125 us per column).
 //   D0:        factor of the first diagonal tile.
 // Ticket order: [D0, HEAD(1)] then for every column g: HEAD(g+2), PLAIN(g+2, g), PRE(g+2),
-// PLAIN(g+3.., g).  Every dependency of a task has a smaller ticket, except that HEAD(g+2) needs
-// the two tickets right behind it; since tickets are handed out in order those are always held
-// by a running CTA (or the next free one), so a spinning CTA only ever waits on running or
-// finished work: deadlock-free for any grid >= 3 without a co-residency requirement.
+// PLAIN(g+3.., g) (in the tail each of them preceded by its split-K parts, see df_split).  Every
+// dependency of a task has a smaller ticket, except that HEAD(g+2) needs the two tiles ticketed right
+// behind it; since tickets are handed out in order those are always held by a running CTA (or the
+// next free one), so a spinning CTA only ever waits on running or finished work: deadlock-free for
+// any grid >= 13 (3 tiles x 4 parts + 1) without a co-residency requirement; smaller grids only occur
+// for matrices too small to be split.
 // --------------------------------------------------------------------------------------
 __device__ __forceinline__ void wait_ready(const int* flag, bool sys = false) {
   if (sys) {
@@ -823,7 +825,9 @@ struct DfArgs {
   double* pool;                   // gridDim.x scratch tiles
   int32_t* info;
   int* ticket; int* ready;        // ready[(b * (nt + nbt) + i) * nt + j]
-  int* pready;                    // pready[b * nt + k]: PRE(k) done
+  int* pcount;                    // pcount[(b * (nt + nbt) + i) * nt + j]: K-parts already subtracted from tile (i, j)
+                                  // (tile (k, k): parts of PRE(k))
+  int grid;                       // CTAs of the launch (enters the split-K rule)
   long long* prof;                // debug: globaltimer stamps of HEAD(nt/2), HEAD(nt/2 + 1) (or null)
   Peers peers;                    // multi-GPU: rank, world and the peers' address deltas (world == 1: unused)
 };
@@ -836,19 +840,54 @@ __device__ __forceinline__ long long globaltimer_ns() {
 
 enum { TASK_D0 = 0, TASK_HEAD = 1, TASK_PLAIN = 2, TASK_PRE = 3 };
 
+// Split-K of the tail.  Towards the end of the sweep a column has fewer tiles than there are SMs while
+// every tile still carries a K-loop over all earlier columns (1.2 ms at n = 8424): SMs run dry.  From the
+// column where fewer than 1.5 tile tasks per SM remain, the K-range of every tile of the group is cut
+// into S <= 4 parts; parts 0 .. S-2 are tasks of their own that accumulate their range and subtract it
+// from the tile (in part order, sequenced by a per-tile counter, so the result does not depend on
+// timing), the last part is the PLAIN / HEAD task itself.  Same function on host (ticket count) and device.
+struct DfShape {
+  int nt, nbt, batch;
+  int grid;   // CTAs of the launch
+  int world;  // ranks sharing the sweep (1 on a single GPU)
+};
+__host__ __device__ __forceinline__ int df_split(const DfShape& sh, int g) {
+  if (g < 24) return 1;  // parts shorter than 6 k-tiles are not worth a read-modify-write of the tile
+  const long r = sh.nt + sh.nbt - g;
+  const long W = r * (r - 1) / 2 * sh.batch / sh.world;  // tile tasks left for this rank
+  const long want = (3L * sh.grid) / 2;
+  if (W >= want) return 1;
+  long s = (want + W - 1) / (W > 0 ? W : 1);
+  if (s > 4) s = 4;
+  while (s > 1 && g / s < 6) --s;
+  return static_cast<int>(s);
+}
+
 // Tasks per matrix: prologue and column group g (see the ticket order above).
 __host__ __device__ __forceinline__ int df_prologue_tasks(int nt) { return nt > 1 ? 2 : 1; }
-__host__ __device__ __forceinline__ int df_group_tasks(int nt, int rows_total, int g) {
+__host__ __device__ __forceinline__ int df_group_tiles(int nt, int rows_total, int g) {
   const int first = (g + 1 < nt) ? g + 2 : g + 1;
   const int nplain = rows_total - first;
   return (nplain > 0 ? nplain : 0) + ((g + 2 < nt) ? 2 : 0);
 }
+__host__ __device__ __forceinline__ int df_group_tasks(const DfShape& sh, int g) {
+  return df_group_tiles(sh.nt, sh.nt + sh.nbt, g) * df_split(sh, g);
+}
+__host__ __device__ __forceinline__ long long df_total_tasks(const DfShape& sh) {
+  long long total = df_prologue_tasks(sh.nt);
+  for (int g = 0; g < sh.nt; ++g) total += df_group_tasks(sh, g);
+  return total * sh.batch;
+}
 
-// ticket -> (kind, matrix b, tile row i, tile column j); HEAD(k) comes back as (i = k, j = k - 1), PRE(k) as (k, k).
-__host__ __device__ __forceinline__ void df_decode(int t, int nt, int nbt, int batch, int& kind, int& b, int& i,
-                                                   int& j) {
-  const int rows_total = nt + nbt;
+// ticket -> (kind, matrix b, tile row i, tile column j, K-part, number of parts); HEAD(k) comes back as
+// (i = k, j = k - 1), PRE(k) as (k, k).  Parts of a tile carry consecutive tickets, the last part last.
+__host__ __device__ __forceinline__ void df_decode(int t, const DfShape& sh, int& kind, int& b, int& i, int& j,
+                                                   int& part, int& nparts) {
+  const int nt = sh.nt, batch = sh.batch;
+  const int rows_total = nt + sh.nbt;
   const int npro = df_prologue_tasks(nt);
+  part = 0;
+  nparts = 1;
   if (t < batch * npro) {
     b = t / npro;
     if (t % npro == 0) { kind = TASK_D0; i = 0; j = 0; } else { kind = TASK_HEAD; i = 1; j = 0; }
@@ -856,12 +895,14 @@ __host__ __device__ __forceinline__ void df_decode(int t, int nt, int nbt, int b
   }
   int rem = t - batch * npro, g = 0, cnt = 0;
   for (;; ++g) {
-    cnt = df_group_tasks(nt, rows_total, g);
+    cnt = df_group_tasks(sh, g);
     if (rem < batch * cnt) break;
     rem -= batch * cnt;
   }
   b = rem / cnt;
-  const int idx = rem % cnt;
+  nparts = df_split(sh, g);
+  const int idx = (rem % cnt) / nparts;
+  part = (rem % cnt) % nparts;
   j = g;
   if (g + 2 < nt) {
     if (idx == 0) { kind = TASK_HEAD; i = g + 2; j = g + 1; }
@@ -872,6 +913,10 @@ __host__ __device__ __forceinline__ void df_decode(int t, int nt, int nbt, int b
     kind = TASK_PLAIN;
     i = ((g + 1 < nt) ? g + 2 : g + 1) + idx;
   }
+}
+
+__device__ __forceinline__ void wait_count(const int* counter, int target) {
+  while (ld_acquire(counter) < target) __nanosleep(40);
 }
 
 template <bool MULTI>
@@ -894,8 +939,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
     const int t = s_task;
     __syncthreads();
     if (t >= p.total_tasks) break;
-    int kind, b, i, j;
-    df_decode(t, p.nt, p.nbt, p.batch, kind, b, i, j);
+    int kind, b, i, j, part, nparts;
+    const DfShape sh = {p.nt, p.nbt, p.batch, p.grid, p.peers.world};
+    df_decode(t, sh, kind, b, i, j, part, nparts);
     // multi-GPU: tile rows are dealt block-cyclically; a rank only runs the tasks of its own rows
     if (multi && ((i / p.peers.row_block) % p.peers.world) != p.peers.rank) continue;
     double* Ab = p.A + (int64_t)b * p.strideA;
@@ -911,21 +957,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
       const int kb = static_cast<int>(min64(TILE, p.n));
       diag_load(smem_raw, Ab, p.lda, kb);
       diag_factor_core<MULTI>(smem_raw, Ab, p.lda, kb, 0, wsb, flags, p.info + b, ready_b, pe, nullptr);
-    } else if (kind == TASK_PRE) {
-      // A_kk -= sum_{l<k-1} L_kl L_kl^T
-      const int k = i;
-      const int kb = static_cast<int>(min64(TILE, p.n - (int64_t)k * TILE));
-      const double* rowk = Ab + (int64_t)k * TILE * p.lda;
-      Acc acc;
-      acc_zero(acc);
-      gemm_nt_mainloop_dep<0>(stages, rowk, p.lda, kb, rowk, p.lda, kb, (k - 1) * TILE, acc,
-                              ready_b + (int64_t)k * p.nt, ready_b + (int64_t)k * p.nt, multi);
-      store_tile<1>(Ab + (int64_t)k * TILE * p.lda + (int64_t)k * TILE, p.lda, kb, kb, acc, true);
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) st_release(p.pready + (int64_t)b * p.nt + k, 1);
     } else {
-      // PLAIN (i, j) and HEAD (k = i, j = k - 1) share the accumulate + solve
+      // PRE (k): A_kk -= sum_{l<k-1} L_kl L_kl^T.  PLAIN (i, j) and HEAD (k = i, j = k - 1): T = A_ij - sum_{l<j}
+      // L_il L_jl^T, then the solve.  The K-range [0, nk) of the tile is cut into `nparts` parts (1 except in
+      // the tail of the sweep); this task accumulates part `part` and subtracts it from the tile once the
+      // earlier parts have done so.
+      const bool pre = kind == TASK_PRE;
+      const int nk = pre ? i - 1 : j;
+      const int k0 = (int)((long)part * nk / nparts), k1 = (int)((long)(part + 1) * nk / nparts);
       const int kb = static_cast<int>(min64(TILE, p.n - (int64_t)j * TILE));
       const double* rowj = Ab + (int64_t)j * TILE * p.lda;
       double* rowi;
@@ -941,15 +980,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
       const int* ready_i = ready_b + (int64_t)i * p.nt;
       const int* ready_j = ready_b + (int64_t)j * p.nt;
       double* T = rowi + (int64_t)j * TILE;
+      int* pcount = p.pcount + ((int64_t)b * rows_total + i) * p.nt + j;
       Acc acc;
-      if (j > 0) {
+      if (k1 > k0) {
         acc_zero(acc);
         // (the masked lower-triangular MODE 1 path is slower than the full tile: its branches break
         //  the DMMA/LDS software pipeline; measured 2x per chunk)
-        gemm_nt_mainloop_dep<0>(stages, rowi, ldi, valid, rowj, p.lda, kb, j * TILE, acc, ready_i, ready_j, multi);
-        store_tile<1>(T, ldi, valid, kb, acc, false);
+        gemm_nt_mainloop_dep<0>(stages, rowi + (int64_t)k0 * TILE, ldi, valid, rowj + (int64_t)k0 * TILE, p.lda, kb,
+                                (k1 - k0) * TILE, acc, ready_i + k0, ready_j + k0, multi);
+        if (part > 0) wait_count(pcount, part);  // parts subtract in order: the rounding does not depend on timing
+        store_tile<1>(T, ldi, valid, kb, acc, pre);
         __threadfence();
         __syncthreads();
+      } else if (part > 0) {
+        wait_count(pcount, part);
+      }
+      if (pre || part + 1 < nparts) {
+        if (tid == 0) st_release(pcount, part + 1);
+        continue;
       }
       if (pf) pf[1] = globaltimer_ns();
       wait_ready(ready_j + j, multi);
@@ -977,7 +1025,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
         const int k = i;
         syrk_from_smem(Xs, acc);
         if (pf) pf[4] = globaltimer_ns();
-        if (k >= 2) wait_ready(p.pready + (int64_t)b * p.nt + k);
+        if (k >= 2)  // every K-part of PRE(k) (ticketed in column group k - 2) has been subtracted
+          wait_count(p.pcount + ((int64_t)b * rows_total + k) * p.nt + k, df_split(sh, k - 2));
         __syncthreads();  // every warp is done reading Xs
         double* Tkk = rowi + (int64_t)k * TILE;
         assemble_diag(Xs, Tkk, p.lda, valid, acc);
@@ -1030,7 +1079,7 @@ static int64_t ws_stride(int64_t nt, int64_t nbt) { return ws_scratch_off(nt) + 
 
 // After the per-matrix regions: [DF_POOL_TILES scratch tiles][int region: ticket (2 ints) + ready flags].
 static int64_t ws_ready_ints(int64_t nt, int64_t nbt, int64_t batch) {
-  return 2 + batch * (nt + nbt) * nt + batch * nt;  // ticket, tile flags, PRE flags
+  return 2 + 2 * batch * (nt + nbt) * nt;  // ticket, tile ready flags, tile K-part counters
 }
 
 extern "C" size_t gpar_potrf_workspace_bytes(int64_t n, int64_t nb, int64_t batch) {
@@ -1074,11 +1123,12 @@ static int launch_dataflow(double* A, int64_t lda, int64_t n, int64_t strideA, d
   p.A = A; p.lda = lda; p.n = n; p.strideA = strideA;
   p.B = B; p.ldb = ldb; p.nb = nb; p.strideB = strideB;
   p.batch = (int)batch; p.nt = nt; p.nbt = nbt;
-  int64_t total = df_prologue_tasks(nt);
-  for (int g = 0; g < nt; ++g) total += df_group_tasks(nt, nt + nbt, g);
-  total *= batch;
+  int grid = num_sms < DF_POOL_TILES ? num_sms : DF_POOL_TILES;
+  const DfShape sh = {nt, nbt, (int)batch, grid, peers.world};
+  const long long total = df_total_tasks(sh);
   if (total > 0x7fffffff) { set_error("gpar_potrf: too many tile tasks"); return -9; }
   p.total_tasks = (int)total;
+  p.grid = grid;
   p.ws = ws; p.strideWs = ws_stride(nt, nbt);
   p.pool = ws + batch * p.strideWs;
   p.info = info;
@@ -1086,10 +1136,9 @@ static int launch_dataflow(double* A, int64_t lda, int64_t n, int64_t strideA, d
   p.peers = peers;
   int* ints = reinterpret_cast<int*>(p.pool + (int64_t)DF_POOL_TILES * TILE * TILE);
   p.ticket = ints; p.ready = ints + 2;
-  p.pready = p.ready + batch * (int64_t)(nt + nbt) * nt;
+  p.pcount = p.ready + batch * (int64_t)(nt + nbt) * nt;
   if (reset) df_reset(ws, n, nb, batch, stream);
-  int grid = num_sms < DF_POOL_TILES ? num_sms : DF_POOL_TILES;
-  if ((int64_t)grid > total) grid = (int)total;
+  if ((long long)grid > total) grid = (int)total;  // (p.grid keeps the nominal size: it only feeds the split rule)
   if (peers.world > 1)
     potrf_dataflow_kernel<true><<<grid, GEMM_THREADS, DF_SMEM_BYTES, stream>>>(p);
   else
@@ -1261,17 +1310,16 @@ static int syrk_impl(double* C, int64_t ldc, int64_t n, int64_t strideC, const d
 }
 
 // Debug / tests: the task list of the dataflow kernel, decoded on the host by the same function the
-// kernel uses.  out4 = {kind (0 D0, 1 HEAD, 2 PLAIN, 3 PRE), matrix, tile row, tile column}; returns the
-// total number of tickets (t < 0: only the count).
-extern "C" int gpar_debug_decode_ticket(int64_t n, int64_t nb, int64_t batch, int64_t t, int32_t* out4) {
+// kernel uses.  out6 = {kind (0 D0, 1 HEAD, 2 PLAIN, 3 PRE), matrix, tile row, tile column, K-part, parts};
+// returns the total number of tickets of a launch with `grid` CTAs (t < 0: only the count).
+extern "C" int gpar_debug_decode_ticket(int64_t n, int64_t nb, int64_t batch, int64_t grid, int64_t t, int32_t* out6) {
   const int nt = (int)((n + TILE - 1) / TILE), nbt = nb > 0 ? (int)((nb + TILE - 1) / TILE) : 0;
-  int64_t total = df_prologue_tasks(nt);
-  for (int g = 0; g < nt; ++g) total += df_group_tasks(nt, nt + nbt, g);
-  total *= batch;
-  if (t >= 0 && t < total && out4) {
-    int kind, b, i, j;
-    df_decode((int)t, nt, nbt, (int)batch, kind, b, i, j);
-    out4[0] = kind; out4[1] = b; out4[2] = i; out4[3] = j;
+  const DfShape sh = {nt, nbt, (int)batch, (int)grid, 1};
+  const long long total = df_total_tasks(sh);
+  if (t >= 0 && t < total && out6) {
+    int kind, b, i, j, part, nparts;
+    df_decode((int)t, sh, kind, b, i, j, part, nparts);
+    out6[0] = kind; out6[1] = b; out6[2] = i; out6[3] = j; out6[4] = part; out6[5] = nparts;
   }
   return (int)total;
 }

@@ -199,10 +199,11 @@ int gpar_debug_latency_probe(double* out, void* stream);
  * around column nt/2 of matrix 0 into prof. */
 int gpar_debug_set_dataflow_prof(long long* prof);
 /* Debug / tests: ticket t of the dataflow kernel's task list for an n x n matrix with nb appended rows, decoded on
- * the host by the function the kernel uses: out4 = {kind (0 first diagonal tile, 1 head = sub-diagonal solve +
- * diagonal factor of tile row out4[2], 2 plain tile, 3 diagonal pre-update), matrix, tile row, tile column}.
+ * the host by the function the kernel uses, for a launch of `grid` CTAs: out6 = {kind (0 first diagonal tile,
+ * 1 head = sub-diagonal solve + diagonal factor of tile row out6[2], 2 plain tile, 3 diagonal pre-update), matrix,
+ * tile row, tile column, K-part, number of K-parts of the tile (split-K in the tail of the sweep)}.
  * Returns the number of tickets. */
-int gpar_debug_decode_ticket(int64_t n, int64_t nb, int64_t batch, int64_t t, int32_t* out4);
+int gpar_debug_decode_ticket(int64_t n, int64_t nb, int64_t batch, int64_t grid, int64_t t, int32_t* out6);
 /* Debug: clock64 phase timestamps (21 values) of the diagonal-tile factor on A[0:128, 0:128]. */
 int gpar_debug_diag_profile(double* A, int64_t lda, int64_t n, double* ws, int32_t* info, long long* prof,
                             void* stream);

@@ -151,8 +151,9 @@ def test_engine_fails_loudly_without_cuda():
 
 
 # ---- task list of the Cholesky dataflow kernel and its multi-GPU partition (host decode, no GPU) ----
-@pytest.mark.parametrize("n,nb,batch", [(100, 0, 1), (128, 1, 1), (300, 1, 1), (1000, 130, 1), (2049, 1, 1), (640, 0, 3)])
-def test_dataflow_task_list_covers_every_tile_once_and_orders_dependencies(n, nb, batch):
+@pytest.mark.parametrize("n,nb,batch,grid", [(100, 0, 1, 148), (128, 1, 1, 148), (300, 1, 1, 148), (1000, 130, 1, 148),
+                                             (2049, 1, 1, 148), (640, 0, 3, 148), (5000, 1, 1, 148), (8424, 1, 1, 148)])
+def test_dataflow_task_list_covers_every_tile_once_and_orders_dependencies(n, nb, batch, grid):
     import ctypes as C
 
     from gpar_b200 import _lib
@@ -160,13 +161,22 @@ def test_dataflow_task_list_covers_every_tile_once_and_orders_dependencies(n, nb
 
     lib = _lib.load()
     nt, nbt = (n + 127) // 128, (nb + 127) // 128 if nb > 0 else 0
-    total = lib.gpar_debug_decode_ticket(n, nb, batch, -1, None)
-    out = (C.c_int32 * 4)()
+    total = lib.gpar_debug_decode_ticket(n, nb, batch, grid, -1, None)
+    out = (C.c_int32 * 6)()
     D0, HEAD, PLAIN, PRE = 0, 1, 2, 3
-    ticket = {}  # (matrix, what, i, j) -> ticket
+    tasks = []
     for t in range(total):
-        lib.gpar_debug_decode_ticket(n, nb, batch, t, out)
-        kind, b, i, j = list(out)
+        lib.gpar_debug_decode_ticket(n, nb, batch, grid, t, out)
+        tasks.append(tuple(out))
+    final = {}  # (matrix, what, i, j) -> ticket of the task that finishes it
+    split_seen = False
+    for t, (kind, b, i, j, part, nparts) in enumerate(tasks):
+        assert 0 <= part < nparts <= 4
+        split_seen |= nparts > 1
+        if part > 0:  # K-parts of a tile carry consecutive tickets, in order
+            assert tasks[t - 1] == (kind, b, i, j, part - 1, nparts)
+        if part + 1 < nparts:
+            continue
         if kind == D0:
             keys = [(b, "diag", 0, 0)]
         elif kind == HEAD:
@@ -179,41 +189,42 @@ def test_dataflow_task_list_covers_every_tile_once_and_orders_dependencies(n, nb
             assert kind == PRE and i == j and i >= 2
             keys = [(b, "pre", i, i)]
         for k in keys:
-            assert k not in ticket, f"{k} scheduled twice"
-            ticket[k] = t
+            assert k not in final, f"{k} scheduled twice"
+            final[k] = t
+    if n >= 5000 and batch == 1:
+        assert split_seen  # the tail of a large sweep is split
     for b in range(batch):
         # coverage: every diagonal tile, every tile below the diagonal (incl. appended rows), PRE for k >= 2
         for k in range(nt):
-            assert (b, "diag", k, k) in ticket
+            assert (b, "diag", k, k) in final
             if k >= 2:
-                assert (b, "pre", k, k) in ticket
+                assert (b, "pre", k, k) in final
         for j in range(nt):
             for i in range(j + 1, nt + nbt):
-                assert (b, "tile", i, j) in ticket
-        # dependencies: a tile task streams L_il, L_jl (l < j) and needs diag j
-        for (bb, what, i, j), t in ticket.items():
-            if bb != b:
-                continue
-            if what == "tile":
-                deps = [(b, "diag", j, j)] + [(b, "tile", i, l) for l in range(j)] + [(b, "tile", j, l) for l in range(j)]
-                head = i < nt and j == i - 1  # solved inside HEAD(i): may wait for the ticket right behind it
-                for d in deps:
-                    if head and d == (b, "tile", i, i - 2):
-                        assert ticket[d] <= t + 2
-                    else:
-                        assert ticket[d] < t, f"{(what, i, j)} depends on later ticket {d}"
-            elif what == "pre":
-                for l in range(i - 1):
-                    assert ticket[(b, "tile", i, l)] < t
-            elif what == "diag" and i >= 2:
-                # the head needs PRE(k) and tile (k, k-2): at most the two tickets right behind it
-                assert ticket[(b, "pre", i, i)] <= t + 2 and ticket[(b, "tile", i, i - 2)] <= t + 2
-    assert len(ticket) == total + batch * max(nt - 1, 0)  # every HEAD ticket carries two entries
-    # multi-GPU partition: a task runs on the owner of its tile row; forward dependencies of a head stay on-rank
+                assert (b, "tile", i, j) in final
+    # dependencies of every task (partial or final): the k-tiles it streams and, for final parts, diag j
+    for t, (kind, b, i, j, part, nparts) in enumerate(tasks):
+        if kind == D0:
+            continue
+        nk = i - 1 if kind == PRE else j
+        k0, k1 = part * nk // nparts, (part + 1) * nk // nparts
+        if nparts > 1:
+            assert k1 - k0 >= 6  # no crumbs
+        deps = [(b, "tile", i, l) for l in range(k0, k1)]
+        if kind != PRE:
+            deps += [(b, "tile", j, l) for l in range(k0, k1)]
+            if part + 1 == nparts:
+                deps.append((b, "diag", j, j))
+        head = kind == HEAD
+        for d in deps:
+            if head and d == (b, "tile", i, i - 2):
+                assert final[d] <= t + 2 * nparts  # the tile ticketed right behind the head (and its parts)
+            else:
+                assert final[d] < t, f"{tasks[t]} depends on later ticket {d}"
+        if head and i >= 2 and part + 1 == nparts:
+            assert final[(b, "pre", i, i)] <= t + 3 * nparts
+    # multi-GPU partition: blocks of GPAR_ROW_BLOCK = 4 tile rows, dealt cyclically
     for world in (2, 3, 8):
-        for (b, what, i, j), t in ticket.items():
-            if what == "diag" and i >= 2:
-                assert tile_row_owner(i, world) == tile_row_owner(i, world)  # head, PRE(i) and tile (i, i-2): row i
         owners = [tile_row_owner(i, world) for i in range(nt + nbt)]
-        assert owners[:4] == [0, 0, 0, 0][: len(owners[:4])]  # blocks of GPAR_ROW_BLOCK = 4 tile rows
+        assert owners[:4] == [0, 0, 0, 0][: len(owners[:4])]
         assert set(owners) == set(range(min(world, (nt + nbt + 3) // 4)))
