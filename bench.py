@@ -370,8 +370,8 @@ def measure_fp64_peaks(eng):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at this shape, from the
-# committed `ncu --set full` capture (profiles/r1_ncu_summary.md): 4.455 GB read + 0.278 GB written.
-NCU_DRAM_BYTES_PER_LAUNCH = 4.455251e9 + 0.277513e9
+# committed `ncu --set full` capture (profiles/r1_ncu_summary.md): 4.332 GB read + 0.289 GB written.
+NCU_DRAM_BYTES_PER_LAUNCH = 4.332022e9 + 0.289156e9
 NCU_DRAM_SOURCE = "ncu --set full capture of potrf_dataflow_kernel at n=8424 (profiles/r1_ncu_summary.md), per launch"
 
 

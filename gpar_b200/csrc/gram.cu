@@ -160,11 +160,13 @@ gram_kernel(const __grid_constant__ gpar_kernel_spec_t spec, const double* __res
 }
 
 // out[j] = sum_i k(Xq[j], Xa[i]) v[i].  One CTA per QT query rows; the a-rows stream through
-// shared memory in chunks of 256 (features built cooperatively).
-constexpr int QT = 8;
+// shared memory in chunks of 256 (features built cooperatively).  QT = 4 keeps the grid above the SM
+// count for the few hundred missing rows of an imputation call and lets three CTAs share an SM
+// (the fp64 exp chains are latency-bound at 8 warps per SM: 0.27 -> 0.1 ms per call at C3).
+constexpr int QT = 4;
 constexpr int AC = 256;
 
-__global__ void __launch_bounds__(AC)
+__global__ void __launch_bounds__(AC, 3)
 gram_gemv_kernel(const __grid_constant__ gpar_kernel_spec_t spec, const double* __restrict__ Xq, int64_t ldq,
                  int64_t nq, const double* __restrict__ Xa, int64_t lda, int64_t na, const double* __restrict__ v,
                  double* __restrict__ out) {

@@ -23,8 +23,8 @@ constexpr int DLD = 132;  // row stride of the tile in shared memory: = 4 (mod 1
                           // fragment loads bank-conflict free; rows stay 16-byte aligned for cp.async
 constexpr int PANEL = 32; // panel width of the in-tile blocked factorisation
 constexpr double REFINE_KAPPA = 1.0e3;  // kappa_inf(L_kk) above which the tile solves are refined
-// shared layout: Ls[TILE][DLD] | rdiag[TILE] | LT[PANEL][PANEL] | red[32] | ints
-constexpr size_t DIAG_SMEM_BYTES = sizeof(double) * (TILE * DLD + TILE + PANEL * PANEL + 32) + 16;
+// shared layout: Ls[TILE][DLD] | rdiag[TILE] | LT[PANEL][PANEL] | red[32] | rowL[TILE] | ints
+constexpr size_t DIAG_SMEM_BYTES = sizeof(double) * (TILE * DLD + TILE + PANEL * PANEL + 32 + TILE) + 16;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
@@ -156,7 +156,7 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
 // free) with rdiag[c0 + j] = 1 / L_jj; every 8 columns the warp arrives on named barrier 1 + j/8,
 // on which the row-solving warps wait.  Returns the 1-based index of the first bad pivot (or 0).
 __device__ __forceinline__ int factor32_warp(double* __restrict__ Ls, double* __restrict__ rdiag,
-                                             double* __restrict__ LT, int c0, int lane) {
+                                             double* __restrict__ LT, double* __restrict__ rowL, int c0, int lane) {
   double a[PANEL];
   const uint32_t row = smem_u32(Ls + (c0 + lane) * DLD + c0);
   const uint32_t lt = smem_u32(LT);
@@ -205,6 +205,11 @@ __device__ __forceinline__ int factor32_warp(double* __restrict__ Ls, double* __
     a[j] = lij;
     if ((j & 7) == 7) named_bar_arrive(1 + (j >> 3), 160);
   }
+  // ||L||_inf bookkeeping: this row's entries inside the block (columns <= row)
+  double sabs = 0.0;
+#pragma unroll
+  for (int j = 0; j < PANEL; ++j) sabs += (j <= lane) ? fabs(a[j]) : 0.0;
+  rowL[c0 + lane] += sabs;
   return bad;
 }
 
@@ -214,7 +219,8 @@ __device__ __forceinline__ int factor32_warp(double* __restrict__ Ls, double* __
 // strict upper triangle), rows inside the panel start as identity rows (the inverse of the block
 // itself falls out), rows below are rows of L.
 __device__ __forceinline__ void panel_solve_warp(double* __restrict__ Ls, const double* __restrict__ rdiag,
-                                                 const double* __restrict__ LT, int c0, int r) {
+                                                 const double* __restrict__ LT, double* __restrict__ rowL, int c0,
+                                                 int r) {
   double x[PANEL];
   const uint32_t row = smem_u32(Ls + r * DLD + c0);
   const uint32_t lt = smem_u32(LT);
@@ -251,6 +257,12 @@ __device__ __forceinline__ void panel_solve_warp(double* __restrict__ Ls, const 
   if (!inblk) {
 #pragma unroll
     for (int q = 0; q < PANEL / 2; ++q) sts_v2f64(row + 16 * q, x[2 * q], x[2 * q + 1]);
+    if (r >= c0 + PANEL) {  // a row of L: its 32 new entries enter ||L||_inf (same thread every panel: no race)
+      double sabs = 0.0;
+#pragma unroll
+      for (int j = 0; j < PANEL; ++j) sabs += fabs(x[j]);
+      rowL[r] += sabs;
+    }
   } else {
     // the diagonal entry is rdiag (already there) and the lower part holds L32: strict upper only
 #pragma unroll
@@ -343,22 +355,24 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
   double* rdiag = Ls + TILE * DLD;
   double* LT = rdiag + TILE;
   double* red = LT + PANEL * PANEL;  // 32 doubles of reduction scratch
-  int* s_int = reinterpret_cast<int*>(red + 32);  // [0] first bad pivot, [1] refine
+  double* rowL = red + 32;           // running row sums of |L| (accumulated panel by panel)
+  int* s_int = reinterpret_cast<int*>(rowL + TILE);  // [0] first bad pivot, [1] refine
   const int tid = threadIdx.x, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
   const int warp = canonical_warp();
   const bool multi = MULTI && (pe != nullptr) && (pe->world > 1);  // MULTI = false: all peer code compiles out
   if (tid == 0) s_int[0] = 0;
+  if (tid < TILE) rowL[tid] = 0.0;
   GPAR_PROF(1);
 #pragma unroll 1
   for (int p = 0; p < TILE / PANEL; ++p) {
     const int c0 = PANEL * p;
     __syncthreads();  // the tile (or the previous rank-32 update) is complete
     if (warp == 0) {
-      const int bad = factor32_warp(Ls, rdiag, LT, c0, lane);
+      const int bad = factor32_warp(Ls, rdiag, LT, rowL, c0, lane);
       if (bad && lane == 0 && s_int[0] == 0) s_int[0] = c0 + bad;
       if (prof && lane == 0) prof[16 + p] = clock64();
     } else if (warp <= 4) {
-      panel_solve_warp(Ls, rdiag, LT, c0, (warp - 1) * 32 + lane);
+      panel_solve_warp(Ls, rdiag, LT, rowL, c0, (warp - 1) * 32 + lane);
       if (prof && lane == 0 && (warp == 1 || warp == 4)) prof[(warp == 1 ? 20 : 24) + p] = clock64();
     }
     __syncthreads();
@@ -369,30 +383,12 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
   __syncthreads();
   GPAR_PROF(10);
 
-  // ---- ||L||_inf: warp per row, lanes along the columns; the 16 rows of a warp are reduced with
-  // independent shuffle chains ----------------------------------------------------------------------
-  {
-    double srow[TILE / 8];
+  // ---- ||L||_inf from the row sums gathered during the sweep (rows >= kb are identity padding) --------
+  if (tid < TILE) {
+    double v = (tid < kb) ? rowL[tid] : 0.0;
 #pragma unroll
-    for (int it = 0; it < TILE / 8; ++it) {
-      const int r = warp + 8 * it, c = 4 * lane;
-      double sv = 0.0;
-      if (c <= r) {
-        const double2 v0 = *reinterpret_cast<const double2*>(Ls + r * DLD + c);
-        const double2 v1 = *reinterpret_cast<const double2*>(Ls + r * DLD + c + 2);
-        sv = fabs(v0.x) + ((c + 1 <= r) ? fabs(v0.y) : 0.0) + ((c + 2 <= r) ? fabs(v1.x) : 0.0) +
-             ((c + 3 <= r) ? fabs(v1.y) : 0.0);
-      }
-      srow[it] = sv;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-      for (int it = 0; it < TILE / 8; ++it) srow[it] += __shfl_xor_sync(0xffffffffu, srow[it], off);
-    double mL = 0.0;
-#pragma unroll
-    for (int it = 0; it < TILE / 8; ++it) mL = fmax(mL, srow[it]);  // rows >= kb are identity rows: harmless
-    if (lane == 0) red[warp] = mL;
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    if (lane == 0) red[warp] = v;
   }
   GPAR_PROF(13);
   // ---- Linv (row major, ld = 128) and its row sums.  Linv[r][c] = Ls[c][r] (c < r), rdiag[r] at
@@ -446,7 +442,7 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
   __syncthreads();
   if (tid == 0) {
     double mL = 0.0, mI = 0.0;
-    for (int i = 0; i < 8; ++i) mL = fmax(mL, red[i]);
+    for (int i = 0; i < 4; ++i) mL = fmax(mL, red[i]);
     for (int i = 0; i < 4; ++i) mI = fmax(mI, red[8 + i]);
     const double kappa = mL * mI;
     const int refine = (kappa > REFINE_KAPPA || !(kappa == kappa)) ? 1 : 0;
@@ -688,7 +684,7 @@ trsm_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const dou
 // dependency of a task has a smaller ticket, except that HEAD(g+2) needs the two tiles ticketed right
 // behind it; since tickets are handed out in order those are always held by a running CTA (or the
 // next free one), so a spinning CTA only ever waits on running or finished work: deadlock-free for
-// any grid >= 13 (3 tiles x 4 parts + 1) without a co-residency requirement; smaller grids only occur
+// any grid >= 3 * GPAR_SPLIT_MAX + 1 (3 tiles x parts + 1) without a co-residency requirement; smaller grids only occur
 // for matrices too small to be split.
 // --------------------------------------------------------------------------------------
 __device__ __forceinline__ void wait_ready(const int* flag, bool sys = false) {
@@ -851,15 +847,24 @@ struct DfShape {
   int grid;   // CTAs of the launch
   int world;  // ranks sharing the sweep (1 on a single GPU)
 };
+#ifndef GPAR_SPLIT_WANT_X10
+#define GPAR_SPLIT_WANT_X10 15  // split once fewer than 1.5 tile tasks per SM remain
+#endif
+#ifndef GPAR_SPLIT_MAX
+#define GPAR_SPLIT_MAX 4
+#endif
+#ifndef GPAR_SPLIT_MINK
+#define GPAR_SPLIT_MINK 6       // k-tiles per part at least
+#endif
 __host__ __device__ __forceinline__ int df_split(const DfShape& sh, int g) {
-  if (g < 24) return 1;  // parts shorter than 6 k-tiles are not worth a read-modify-write of the tile
+  if (g < 4 * GPAR_SPLIT_MINK) return 1;  // short parts are not worth a read-modify-write of the tile
   const long r = sh.nt + sh.nbt - g;
   const long W = r * (r - 1) / 2 * sh.batch / sh.world;  // tile tasks left for this rank
-  const long want = (3L * sh.grid) / 2;
+  const long want = (long)sh.grid * GPAR_SPLIT_WANT_X10 / 10;
   if (W >= want) return 1;
   long s = (want + W - 1) / (W > 0 ? W : 1);
-  if (s > 4) s = 4;
-  while (s > 1 && g / s < 6) --s;
+  if (s > GPAR_SPLIT_MAX) s = GPAR_SPLIT_MAX;
+  while (s > 1 && g / s < GPAR_SPLIT_MINK) --s;
   return static_cast<int>(s);
 }
 

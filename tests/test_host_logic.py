@@ -171,7 +171,7 @@ def test_dataflow_task_list_covers_every_tile_once_and_orders_dependencies(n, nb
     final = {}  # (matrix, what, i, j) -> ticket of the task that finishes it
     split_seen = False
     for t, (kind, b, i, j, part, nparts) in enumerate(tasks):
-        assert 0 <= part < nparts <= 4
+        assert 0 <= part < nparts <= 8
         split_seen |= nparts > 1
         if part > 0:  # K-parts of a tile carry consecutive tickets, in order
             assert tasks[t - 1] == (kind, b, i, j, part - 1, nparts)
@@ -209,7 +209,7 @@ def test_dataflow_task_list_covers_every_tile_once_and_orders_dependencies(n, nb
         nk = i - 1 if kind == PRE else j
         k0, k1 = part * nk // nparts, (part + 1) * nk // nparts
         if nparts > 1:
-            assert k1 - k0 >= 6  # no crumbs
+            assert k1 - k0 >= 3  # no crumbs
         deps = [(b, "tile", i, l) for l in range(k0, k1)]
         if kind != PRE:
             deps += [(b, "tile", j, l) for l in range(k0, k1)]
