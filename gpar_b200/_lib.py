@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("GPAR_B200_LIB") or os.path.join(_HERE, "libgpar_b200.
 TILE = 128
 MAX_TERMS = 8
 MAX_FEATS = 96
+GRAD_NP = 2 * MAX_TERMS + 2 * MAX_FEATS + 1
 TERM_EQ, TERM_RQ, TERM_LINEAR, TERM_CONST = 0, 1, 2, 3
 FEAT_SCALE, FEAT_SIN, FEAT_COS = 0, 1, 2
 
@@ -70,6 +71,10 @@ SIGNATURES = {
     "gpar_trsm_rows": (_int, [_p, _i64, _i64, _p, _p, _i64, _i64, _p, _p]),
     "gpar_syrk_sub": (_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p]),
     "gpar_syrk_add": (_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p]),
+    "gpar_potri_scratch_bytes": (C.c_size_t, [_i64]),
+    "gpar_potri": (_int, [_p, _i64, _i64, _p, _p, _i64, _p, _i64, _p, _p]),
+    "gpar_gram_grad_workspace_bytes": (C.c_size_t, [_i64]),
+    "gpar_gram_grad": (_int, [_SPEC, _p, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p]),
     "gpar_transpose_scale": (_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
     "gpar_vfe_rowterms": (_int, [_SPEC, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p]),
     "gpar_backsolve": (_int, [_p, _i64, _i64, _p, _p, _p, _p, _p]),

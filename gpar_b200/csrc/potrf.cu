@@ -581,6 +581,7 @@ struct SubArgs {
   const double* Aop; int64_t lda; int64_t strideA;
   const double* Bop; int64_t ldb; int64_t strideB;
   int K; int lower; int nt_rows1; int add;  // add != 0: C += A B^T instead of C -= A B^T
+  int tri_k;  // != 0: both operands are UPPER triangular (zero for k < row): tile (ti, tj) starts at k = ti * 128
   // secondary row space (appended rows, row tiles >= nt_rows1): all column tiles
   double* C2; int64_t ldc2; int64_t c_rows2; int64_t strideC2;
   const double* Aop2; int64_t lda2; int64_t strideA2;
@@ -616,7 +617,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_sub_kernel(const SubArgs
   }
   Acc acc;
   acc_zero(acc);
-  gemm_nt_mainloop<0>(stages, Ap, lda, rows, Bp, p.ldb, cols, p.K, acc);
+  const int kstart = (p.tri_k && !second) ? ti * TILE : 0;
+  gemm_nt_mainloop<0>(stages, Ap + kstart, lda, rows, Bp + kstart, p.ldb, cols, p.K - kstart, acc);
   if (p.add) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -661,6 +663,56 @@ trsm_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const dou
     __threadfence();
     __syncthreads();
   }
+}
+
+// --------------------------------------------------------------------------------------
+// U = L^-T (upper triangular, row major) for the inverse A^-1 = U U^T of the fit gradients: the
+// sweep of trsm_rows_kernel applied to the identity, with the structure exploited -- row block ti
+// of I L^-T is zero left of column block ti, so the sweep and every K-loop start there (n^3 / 3
+// instead of n^3 flops) -- and 32-row CTAs (4 per 128-row block: the rows of a block are
+// independent) so that 4 nt CTAs share the work instead of nt.
+// --------------------------------------------------------------------------------------
+constexpr int TRTRI_ROWS = 32;
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+trtri_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const double* __restrict__ ws,
+                  double* __restrict__ U, int64_t ldu, double* __restrict__ scratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
+  pipe_init();
+  constexpr int SUB = TILE / TRTRI_ROWS;
+  // heaviest row blocks first: block 0 sweeps every column, the last block only its own
+  const int ti = blockIdx.x / SUB, sub = blockIdx.x % SUB;
+  const int64_t row0 = (int64_t)ti * TILE + sub * TRTRI_ROWS;
+  if (row0 >= n) return;
+  double* Brow = U + row0 * ldu;
+  const int valid = static_cast<int>(min64(TRTRI_ROWS, n - row0));
+  const int nt = static_cast<int>((n + TILE - 1) / TILE);
+  const double* flags = ws + (int64_t)nt * TILE * TILE;
+  for (int j = ti; j < nt; ++j) {
+    const int kb = static_cast<int>(min64(TILE, n - (int64_t)j * TILE));
+    if (j > ti) {
+      Acc acc;
+      acc_zero(acc);
+      gemm_nt_mainloop(stages, Brow + (int64_t)ti * TILE, ldu, valid,
+                       L + (int64_t)j * TILE * ldl + (int64_t)ti * TILE, ldl, kb, (j - ti) * TILE, acc);
+      store_tile<1>(Brow + (int64_t)j * TILE, ldu, valid, kb, acc, false);
+      __threadfence();
+      __syncthreads();
+    }
+    Acc xacc;
+    tile_solve(stages, Brow + (int64_t)j * TILE, ldu, valid, kb, ws + (int64_t)j * TILE * TILE,
+               L + (int64_t)j * TILE * ldl + (int64_t)j * TILE, ldl, flags[j] != 0.0,
+               scratch + (int64_t)blockIdx.x * TILE * TILE, xacc);
+    __threadfence();
+    __syncthreads();
+  }
+}
+
+__global__ void set_identity_kernel(double* __restrict__ U, int64_t ldu, int64_t n) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * ldu) return;
+  const int64_t r = idx / ldu, c = idx % ldu;
+  U[idx] = (r == c) ? 1.0 : 0.0;
 }
 
 // --------------------------------------------------------------------------------------
@@ -1067,6 +1119,7 @@ static void set_smem_attrs() {
   cudaFuncSetAttribute(trsm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
   cudaFuncSetAttribute(gemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
   cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
+  cudaFuncSetAttribute(trtri_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
   cudaFuncSetAttribute(potrf_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM_BYTES);
   cudaFuncSetAttribute(potrf_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM_BYTES);
   done = true;
@@ -1200,7 +1253,7 @@ extern "C" int gpar_potrf(double* A, int64_t lda, int64_t n, int64_t strideA, do
       p.C = A + (j0 + TILE) * lda + (j0 + TILE); p.ldc = lda; p.c_rows = below; p.c_cols = below; p.strideC = strideA;
       p.Aop = A + (j0 + TILE) * lda + j0; p.lda = lda; p.strideA = strideA;
       p.Bop = p.Aop; p.ldb = lda; p.strideB = strideA;
-      p.K = kb; p.lower = 1; p.nt_rows1 = ntr; p.add = 0;
+      p.K = kb; p.lower = 1; p.nt_rows1 = ntr; p.add = 0; p.tri_k = 0;
       p.C2 = nb > 0 ? B + (j0 + TILE) : nullptr; p.ldc2 = ldb; p.c_rows2 = nb; p.strideC2 = strideB;
       p.Aop2 = nb > 0 ? B + j0 : nullptr; p.lda2 = ldb; p.strideA2 = strideB;
       gemm_sub_kernel<<<dim3((unsigned)ntr, (unsigned)(ntr + nbt), (unsigned)batch), GEMM_THREADS, GEMM_SMEM_BYTES,
@@ -1282,7 +1335,7 @@ extern "C" int gpar_trsm_rows(const double* L, int64_t ldl, int64_t n, const dou
 }
 
 static int syrk_impl(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw, int64_t k,
-                     int64_t strideW, int64_t batch, int add, void* stream_);
+                     int64_t strideW, int64_t batch, int add, void* stream_, int tri_k = 0);
 
 extern "C" int gpar_syrk_sub(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw,
                              int64_t k, int64_t strideW, int64_t batch, void* stream_) {
@@ -1295,7 +1348,7 @@ extern "C" int gpar_syrk_add(double* C, int64_t ldc, int64_t n, int64_t strideC,
 }
 
 static int syrk_impl(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw, int64_t k,
-                     int64_t strideW, int64_t batch, int add, void* stream_) {
+                     int64_t strideW, int64_t batch, int add, void* stream_, int tri_k) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!C || !aligned16(C) || (ldc & 1) || ldc < n) { set_error("gpar_syrk_sub: bad C"); return -1; }
   if (!W || !aligned16(W) || (ldw & 1) || ldw < k) { set_error("gpar_syrk_sub: bad W"); return -5; }
@@ -1308,10 +1361,36 @@ static int syrk_impl(double* C, int64_t ldc, int64_t n, int64_t strideC, const d
   p.C = C; p.ldc = ldc; p.c_rows = n; p.c_cols = n; p.strideC = strideC;
   p.Aop = W; p.lda = ldw; p.strideA = strideW;
   p.Bop = W; p.ldb = ldw; p.strideB = strideW;
-  p.K = (int)k; p.lower = 1; p.nt_rows1 = (int)nt; p.add = add;
+  p.K = (int)k; p.lower = 1; p.nt_rows1 = (int)nt; p.add = add; p.tri_k = tri_k;
   p.C2 = nullptr; p.ldc2 = 0; p.c_rows2 = 0; p.strideC2 = 0; p.Aop2 = nullptr; p.lda2 = 0; p.strideA2 = 0;
   gemm_sub_kernel<<<dim3(nt, nt, (unsigned)batch), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
   return check_launch("gpar_syrk_sub");
+}
+
+// K10 -- A^-1 from the factor (gradients of the log-marginal): U <- L^-T, Ainv (lower) <- U U^T.
+extern "C" size_t gpar_potri_scratch_bytes(int64_t n) {
+  if (n <= 0) return 0;
+  return (size_t)((n + TILE - 1) / TILE) * (TILE / TRTRI_ROWS) * TILE * TILE * sizeof(double);
+}
+
+extern "C" int gpar_potri(const double* L, int64_t ldl, int64_t n, const double* ws, double* U, int64_t ldu,
+                          double* Ainv, int64_t lda, double* scratch, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!L || !aligned16(L) || (ldl & 1) || ldl < n) { set_error("gpar_potri: bad L"); return -1; }
+  if (!ws || !aligned16(ws)) return -4;
+  if (n <= 0) return 0;
+  if (!U || !aligned16(U) || (ldu & 1) || ldu < n) { set_error("gpar_potri: bad U"); return -5; }
+  if (!Ainv || !aligned16(Ainv) || (lda & 1) || lda < n) { set_error("gpar_potri: bad Ainv"); return -7; }
+  if (!scratch || !aligned16(scratch)) { set_error("gpar_potri: bad scratch"); return -9; }
+  set_smem_attrs();
+  const int64_t total = n * ldu;
+  set_identity_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(U, ldu, n);
+  const unsigned nt = (unsigned)((n + TILE - 1) / TILE);
+  trtri_rows_kernel<<<nt * (TILE / TRTRI_ROWS), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(L, ldl, n, ws, U, ldu, scratch);
+  cudaMemsetAsync(Ainv, 0, sizeof(double) * (size_t)n * lda, stream);
+  int rc = syrk_impl(Ainv, lda, n, 0, U, ldu, n, 0, 1, 1, stream_, 1);
+  if (rc) return rc;
+  return check_launch("gpar_potri");
 }
 
 // Debug / tests: the task list of the dataflow kernel, decoded on the host by the same function the

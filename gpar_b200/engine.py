@@ -144,6 +144,30 @@ class Engine:
         self.launches += 1
         self.flops += batch * float(n) ** 2 * k
 
+    # -- K10 ------------------------------------------------------------------
+    def potri(self, L, ldl, n, ws):
+        """A^-1 (lower triangle, leading dimension ldl) from the factor L and the workspace of its potrf."""
+        U = self.empty(max(n, 1) * ldl)
+        Ainv = self.empty(max(n, 1) * ldl)
+        scratch = self.empty(max(self.lib.gpar_potri_scratch_bytes(n) // 8, 2))
+        rc = self.lib.gpar_potri(self.addr(L), ldl, n, self.addr(ws), self.addr(U), ldl, self.addr(Ainv), ldl,
+                                 self.addr(scratch), self.stream)
+        check(rc, "gpar_potri")
+        self.launches += 3
+        self.flops += 2.0 * n ** 3 / 3.0
+        return Ainv
+
+    def gram_grad(self, spec, X, ldx, n, alpha, Ainv, lda, dvec=None):
+        """Raw chain-rule sums of d LML / d spec (device tensor of _lib.GRAD_NP doubles)."""
+        wsg = self.empty(max(self.lib.gpar_gram_grad_workspace_bytes(n) // 8, 2))
+        out = self.empty(_lib.GRAD_NP)
+        rc = self.lib.gpar_gram_grad(C.byref(spec), self.addr(X), ldx, n, self.addr(alpha), self.addr(Ainv), lda,
+                                     None if dvec is None else self.addr(dvec), self.addr(wsg), self.addr(out),
+                                     self.stream)
+        check(rc, "gpar_gram_grad")
+        self.launches += 2
+        return out
+
     # -- K8 -------------------------------------------------------------------
     def transpose_scale(self, src, lds, rows, cols, scale, dst, ldd):
         rc = self.lib.gpar_transpose_scale(self.addr(src), lds, rows, cols, None if scale is None else self.addr(scale),

@@ -332,9 +332,12 @@ class GPAR:
 
     # -- logpdf -----------------------------------------------------------------
     def logpdf(self, x, y, w, only_last_layer=False, sample_missing=False, return_inputs=False, x_ind=None,
-               outputs=None, normals=None):
+               outputs=None, normals=None, grad_out=None):
         """Log-density of ``y`` (model.py:178-243).  ``normals``: list of host arrays,
-        one per layer that has missing rows, consumed when ``sample_missing``."""
+        one per layer that has missing rows, consumed when ``sample_missing``.  ``grad_out``: a dict
+        that receives, for the LAST layer evaluated, the raw chain-rule sums of the gradient of its
+        log-marginal w.r.t. its kernel spec and noise (``raw``, device tensor; ``layer``) -- what
+        ``GPARRegressor.fit`` feeds to L-BFGS instead of the reference's autograd pass."""
         if self.sparse:
             from .sparse import logpdf_sparse
 
@@ -376,6 +379,14 @@ class GPAR:
                 if want_lp:
                     fac.logdet_quad(out2, 2 * li, fac.n_blk, fac.n_obs)
                     counts.append((li, fac.n_a))
+                    if grad_out is not None and is_last and fac.n_a > 0:
+                        if fac.n_blk != 0 or fac.n_ext != 0:
+                            raise NotImplementedError("gradients are implemented for prior layers only")
+                        Ainv = eng.potri(fac.J, fac.ld, fac.n_obs, fac.ws)
+                        dvec = eng.to_device(1.0 / w_i[avail])
+                        grad_out["raw"] = eng.gram_grad(layer.spec, fac.X, fac.ldx, fac.n_obs, fac.alpha(), Ainv,
+                                                        fac.ld, dvec)
+                        grad_out["layer"] = layer
                 if do_sample:
                     n_m = ext.n
                     z = normals.pop(0) if normals is not None else np.random.standard_normal(n_m)

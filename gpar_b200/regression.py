@@ -5,7 +5,7 @@ import numpy as np
 from scipy.optimize import minimize
 
 from .model import GPAR, per_output
-from .spec import LayerModel, Vars, model_terms
+from .spec import LayerModel, Vars, model_terms, named_gradients
 
 __all__ = ["GPARRegressor", "log_transform", "squishing_transform"]
 
@@ -106,7 +106,8 @@ class GPARRegressor:
     def fit(self, x, y, w=None, greedy=False, fix=True, **kw_args):
         """Layer-wise maximum likelihood (regression.py:391-459).  ``iters`` and other
         keyword arguments go to the L-BFGS-B driver.  Gradients are finite differences
-        of the device log-marginal (analytic gradient kernels are SURVEY 8(f)-1)."""
+        of the device log-marginal for the joint objective (``fix=False``) and inducing-point
+        layers, analytic (``gpar_potri`` + ``gpar_gram_grad``) for the default layer-wise objective."""
         self.condition(x, y, w)
         if greedy:
             raise NotImplementedError("Greedy search is not implemented yet.")
@@ -122,21 +123,38 @@ class GPARRegressor:
                 ctor()
             names = self.vs.match([f"{pi}/*"] if fix else [f"{i}/*" for i in range(pi + 1)])
 
+            # Analytic gradients for the default layer-wise objective on dense layers:
+            # d LML / d theta = sum_ij W_ij dA_ij / d theta with W = 1/2 (alpha alpha^T - A^-1), evaluated
+            # on the device (gpar_potri + gpar_gram_grad) and pushed through the bound transform here.
+            # The joint objective (fix=False: inputs depend on earlier layers' hyper-parameters) and
+            # inducing-point layers keep finite differences.
+            analytic = fix and self.x_ind is None and kw_args.pop("analytic", True)
+
             def objective(z):
                 self.vs.set_latent_vector(names, z)
                 gpar = _construct_gpar(self, self.vs, self.m, pi + 1)
+                g = {} if analytic else None
                 try:
                     if fix:
                         val = -gpar.logpdf(fixed_x, y_cached, None, only_last_layer=True, outputs=[pi],
-                                           x_ind=fixed_x_ind)
+                                           x_ind=fixed_x_ind, grad_out=g)
                     else:
                         val = -gpar.logpdf(self.x, y_cached, None, only_last_layer=False)
                 except Exception:
-                    return 1e300
-                return val if np.isfinite(val) else 1e300
+                    return (1e300, np.zeros_like(z)) if analytic else 1e300
+                if not np.isfinite(val):
+                    return (1e300, np.zeros_like(z)) if analytic else 1e300
+                if not analytic:
+                    return val
+                if "raw" not in g:  # no observation in this layer: constant objective
+                    return val, np.zeros_like(z)
+                grads = named_gradients(g["layer"].terms, g["raw"].cpu().numpy(), noise_name=f"{pi}/noise")
+                gz = -self.vs.latent_gradient(names, grads)
+                return val, np.where(np.isfinite(gz), gz, 0.0)
 
             z0 = self.vs.get_latent_vector(names)
-            res = minimize(objective, z0, method="L-BFGS-B", options={"maxiter": iters, **kw_args})
+            res = minimize(objective, z0, jac=bool(analytic), method="L-BFGS-B",
+                           options={"maxiter": iters, **kw_args})
             self.vs.set_latent_vector(names, res.x)
 
     def logpdf(self, x, y, w=None, sample_missing=False, posterior=False, normals=None):

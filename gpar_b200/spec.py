@@ -7,7 +7,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["determine_indices", "vector_from_init", "Vars", "model_terms", "lower_terms", "LayerModel"]
+__all__ = ["determine_indices", "vector_from_init", "Vars", "model_terms", "lower_terms", "term_gradients",
+           "named_gradients", "LayerModel"]
 
 
 def determine_indices(m, pi, markov):
@@ -91,6 +92,21 @@ class Vars:
                 out.append(np.log(t) - np.log1p(-t))
         return np.concatenate(out) if out else np.zeros(0)
 
+    def latent_gradient(self, names, grads):
+        """Chain rule through the bound transform: ``grads`` maps variable name -> d f / d value
+        (missing names count as zero); returns d f / d z in the packing order of
+        :meth:`get_latent_vector`."""
+        out = []
+        for n in names:
+            v = np.atleast_1d(self._values[n]).astype(np.float64)
+            g = np.atleast_1d(np.asarray(grads.get(n, np.zeros_like(v)), dtype=np.float64)).reshape(v.shape)
+            b = self._bounds[n]
+            if b is not None:
+                lo, hi = b
+                g = g * (v - lo) * (hi - v) / (hi - lo)
+            out.append(g.reshape(-1))
+        return np.concatenate(out) if out else np.zeros(0)
+
     def set_latent_vector(self, names, z):
         i = 0
         for n in names:
@@ -117,32 +133,42 @@ def model_terms(vs, m, pi, scale, scale_tie, per, per_period, per_scale, per_dec
     scales = vs.bnd(name=f"{0 if scale_tie else pi}/input/scales", init=vector_from_init(scale, m))
     if rq:
         alpha = vs.bnd(name=f"{pi}/input/alpha", init=1e-2, lower=1e-3, upper=1e3)
-        terms.append(dict(type="rq", variance=variance, cols=m_inds, scales=scales, alpha=alpha))
+        terms.append(dict(type="rq", variance=variance, cols=m_inds, scales=scales, alpha=alpha,
+                          names=dict(variance=f"{pi}/input/var", scales=f"{0 if scale_tie else pi}/input/scales",
+                                     alpha=f"{pi}/input/alpha")))
     else:
-        terms.append(dict(type="eq", variance=variance, cols=m_inds, scales=scales))
+        terms.append(dict(type="eq", variance=variance, cols=m_inds, scales=scales,
+                          names=dict(variance=f"{pi}/input/var", scales=f"{0 if scale_tie else pi}/input/scales")))
     if per:
         variance = vs.bnd(name=f"{pi}/input/per/var", init=1.0)
         scales = vs.bnd(name=f"{pi}/input/per/scales", init=vector_from_init(per_scale, 2 * m))
         periods = vs.bnd(name=f"{pi}/input/per/pers", init=vector_from_init(per_period, m))
         decays = vs.bnd(name=f"{pi}/input/per/decay", init=vector_from_init(per_decay, m))
         terms.append(dict(type="periodic", variance=variance, cols=m_inds, scales=scales, periods=periods,
-                          decays=decays))
+                          decays=decays,
+                          names=dict(variance=f"{pi}/input/per/var", scales=f"{pi}/input/per/scales",
+                                     periods=f"{pi}/input/per/pers", decays=f"{pi}/input/per/decay")))
     if input_linear:
         scales = vs.bnd(name=f"{pi}/input/lin/scales", init=vector_from_init(input_linear_scale, m))
         const = vs.get(name=f"{pi}/input/lin/const", init=1.0)
-        terms.append(dict(type="linear", variance=1.0, cols=m_inds, scales=scales))
-        terms.append(dict(type="const", variance=const))
+        terms.append(dict(type="linear", variance=1.0, cols=m_inds, scales=scales,
+                          names=dict(scales=f"{pi}/input/lin/scales")))
+        terms.append(dict(type="const", variance=const, names=dict(variance=f"{pi}/input/lin/const")))
     if linear and pi > 0:
         scales = vs.bnd(name=f"{pi}/output/lin/scales", init=vector_from_init(linear_scale, p_num))
-        terms.append(dict(type="linear", variance=1.0, cols=p_inds, scales=scales))
+        terms.append(dict(type="linear", variance=1.0, cols=p_inds, scales=scales,
+                          names=dict(scales=f"{pi}/output/lin/scales")))
     if nonlinear and pi > 0:
         variance = vs.bnd(name=f"{pi}/output/nonlin/var", init=1.0)
         scales = vs.bnd(name=f"{pi}/output/nonlin/scales", init=vector_from_init(nonlinear_scale, p_num))
         if rq:
             alpha = vs.bnd(name=f"{pi}/output/nonlin/alpha", init=1e-2, lower=1e-3, upper=1e3)
-            terms.append(dict(type="rq", variance=variance, cols=p_inds, scales=scales, alpha=alpha))
+            terms.append(dict(type="rq", variance=variance, cols=p_inds, scales=scales, alpha=alpha,
+                              names=dict(variance=f"{pi}/output/nonlin/var", scales=f"{pi}/output/nonlin/scales",
+                                         alpha=f"{pi}/output/nonlin/alpha")))
         else:
-            terms.append(dict(type="eq", variance=variance, cols=p_inds, scales=scales))
+            terms.append(dict(type="eq", variance=variance, cols=p_inds, scales=scales,
+                              names=dict(variance=f"{pi}/output/nonlin/var", scales=f"{pi}/output/nonlin/scales")))
     noise_variance = vs.bnd(name=f"{pi}/noise", init=vector_from_init(noise, pi + 1)[pi], lower=1e-8)
     return terms, float(noise_variance)
 
@@ -198,6 +224,73 @@ def lower_terms(terms):
         nt += 1
     spec.n_terms, spec.n_feats = nt, nf
     return spec
+
+
+def term_gradients(terms, raw):
+    """Finish the chain rule of ``gpar_gram_grad``: ``raw`` is its output vector (layout in
+    include/gpar_b200.h), ``terms`` the term list the spec was lowered from.  Returns one dict per term
+    with the derivative of the log-marginal w.r.t. each of its fields (``variance``, ``scales``,
+    ``alpha``, ``periods``, ``decays``), walking the terms exactly as :func:`lower_terms` does."""
+    raw = np.asarray(raw, dtype=np.float64)
+    base = 2 * _lib.MAX_TERMS
+    out = []
+    nf = nt = 0
+    for t in terms:
+        kind = t["type"]
+        cols = list(t.get("cols", []))
+        g = {}
+        if kind != "const" and len(cols) == 0:
+            out.append(g)
+            continue
+        g["variance"] = raw[2 * nt]
+        if kind == "rq":
+            g["alpha"] = raw[2 * nt + 1]
+
+        def d_da(f, a):  # d LML / d a_f
+            s1 = raw[base + 2 * f]
+            return 2.0 * s1 / a if kind == "linear" else -s1 / a
+
+        if kind == "periodic":
+            m = len(cols)
+            scales = np.asarray(t["scales"], dtype=np.float64).reshape(-1)
+            periods = np.asarray(t["periods"], dtype=np.float64).reshape(-1)
+            decays = np.asarray(t["decays"], dtype=np.float64).reshape(-1)
+            gs, gp, gd = np.zeros(2 * m), np.zeros(m), np.zeros(m)
+            for j in range(m):  # sin block, cos block, decay block
+                for blk in range(2):
+                    f = nf + blk * m + j
+                    a = 1.0 / scales[blk * m + j]
+                    gs[blk * m + j] = d_da(f, a) * (-a * a)           # a = 1 / s
+                    gp[j] += -raw[base + 2 * f + 1] * (-2.0 * math.pi / periods[j] ** 2)  # b = 2 pi / T
+                f = nf + 2 * m + j
+                a = 1.0 / decays[j]
+                gd[j] = d_da(f, a) * (-a * a)
+            g["scales"], g["periods"], g["decays"] = gs, gp, gd
+            nf += 3 * m
+        elif kind != "const":
+            scales = np.asarray(t["scales"], dtype=np.float64).reshape(-1)
+            gs = np.zeros(len(cols))
+            for j in range(len(cols)):
+                a = 1.0 / scales[j]
+                gs[j] = d_da(nf + j, a) * (-a * a)
+            g["scales"] = gs
+            nf += len(cols)
+        out.append(g)
+        nt += 1
+    return out
+
+
+def named_gradients(terms, raw, noise_name=None):
+    """d LML / d (named hyper-parameter) from the raw sums: fields of several terms that share a
+    variable (``scale_tie``) add up; the noise variance takes the diagonal term (dvec = 1 / w)."""
+    grads = {}
+    for t, g in zip(terms, term_gradients(terms, raw)):
+        for field, name in t.get("names", {}).items():
+            if field in g:
+                grads[name] = grads.get(name, 0.0) + np.asarray(g[field], dtype=np.float64)
+    if noise_name is not None:
+        grads[noise_name] = np.asarray(raw, dtype=np.float64)[_lib.GRAD_NP - 1]
+    return grads
 
 
 class LayerModel:

@@ -144,6 +144,25 @@ int gpar_syrk_sub(double* C, int64_t ldc, int64_t n, int64_t strideC, const doub
 int gpar_syrk_add(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw, int64_t k,
                   int64_t strideW, int64_t batch, void* stream);
 
+/* K10 -- gradients of the dense log-marginal for `fit` (regression.py:434-459; the reference differentiates
+ * through Gram + Cholesky + solve with torch autograd):  d LML / d theta = sum_ij W_ij dA_ij / d theta,
+ * W = 1/2 (alpha alpha^T - A^-1).
+ * gpar_potri: U (n x n work matrix) <- L^-T, Ainv (n x n, lower) <- U U^T = A^-1, given L and the `ws` of its
+ * gpar_potrf; scratch = gpar_potri_scratch_bytes(n).
+ * gpar_gram_grad: one pass over the lower triangle of Ainv accumulates the raw sums of the chain rule for every
+ * term and feature of `spec` into out[GPAR_GRAD_NP] (layout: out[2t] variance of term t, out[2t+1] RQ alpha,
+ * out[16+2f] / out[16+2f+1] the a- / b-parameter of feature f, out[208] the diagonal term sum_i W_ii dvec_i;
+ * exact definitions at gram_grad_kernel in csrc/gram.cu, chain rule in gpar_b200/spec.py).  Partial sums are
+ * combined in a fixed order (bitwise reproducible).  workspace = gpar_gram_grad_workspace_bytes(n). */
+#define GPAR_GRAD_NP (2 * GPAR_MAX_TERMS + 2 * GPAR_MAX_FEATS + 1)
+size_t gpar_potri_scratch_bytes(int64_t n);
+int gpar_potri(const double* L, int64_t ldl, int64_t n, const double* ws, double* U, int64_t ldu, double* Ainv,
+               int64_t lda, double* scratch, void* stream);
+size_t gpar_gram_grad_workspace_bytes(int64_t n);
+int gpar_gram_grad(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t n, const double* alpha,
+                   const double* Ainv, int64_t lda, const double* dvec, double* workspace, double* out,
+                   void* stream);
+
 /* K8 -- VFE (Titsias) helpers for `PseudoObs` (model.py:286-287).
  * gpar_transpose_scale: dst (cols x rows) = (diag(scale) src)^T, scale may be NULL.
  * gpar_vfe_rowterms: out[0] = sum_j (k_jj - ||Bt_j||^2)/sigma_j + log(2 pi sigma_j) + y_j^2/sigma_j
