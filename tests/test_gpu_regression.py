@@ -200,3 +200,28 @@ def test_full_size_properties_c3_layer():
     # residual of the linear system: K alpha + (d + eps) alpha = y
     res = b + (0.1 + 1e-12) * alpha.cpu().numpy()[:n] - y
     assert np.max(np.abs(res)) <= 1e-8
+
+
+@pytest.mark.parametrize("name", ["c3_small", "c2_small", "rq_per_small"])
+def test_engine_matches_committed_oracle_fixture(name):
+    """The CUDA path against tests/golden/oracle_small.npz (oracle outputs, scripts/make_golden.py):
+    logpdf rel <= 1e-9, predictive means rel <= 1e-6 with the injected normals of the fixture."""
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "scripts"))
+    import bench
+    import make_golden
+    from gpar_b200 import GPARRegressor
+
+    gold = np.load(os.path.join(root, "tests", "golden", "oracle_small.npz"))
+    data_kw, reg_kw = make_golden.CASES[name]
+    data = bench.make_data(**data_kw)
+    reg = GPARRegressor(**reg_kw)
+    reg.condition(data["x"], data["y"])
+    lp = reg.logpdf(data["x"], data["y"])
+    mean = reg.predict(data["xs"], num_samples=data_kw["S"], normals={"Z": data["Z"]})
+    assert abs(lp - gold[f"{name}/logpdf"]) <= 1e-9 * abs(gold[f"{name}/logpdf"])
+    ref = gold[f"{name}/mean"]
+    assert np.max(np.abs(mean - ref)) <= 1e-6 * np.max(np.abs(ref))

@@ -90,3 +90,19 @@ DETERMINE_GOLDEN = [
 @pytest.mark.parametrize("args,expected", DETERMINE_GOLDEN)
 def test_determine_indices_golden(args, expected):
     assert determine_indices(*args) == expected
+
+
+# ---- committed oracle outputs on small seeded workloads (scripts/make_golden.py) -------------------
+def test_oracle_matches_committed_fixture():
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "scripts"))
+    import make_golden
+
+    gold = np.load(os.path.join(root, "tests", "golden", "oracle_small.npz"))
+    for name in make_golden.CASES:
+        got = make_golden.run(name)
+        for k, v in got.items():
+            np.testing.assert_allclose(v, gold[k], rtol=1e-9, atol=1e-10, err_msg=k)
