@@ -271,20 +271,25 @@ __device__ __forceinline__ void panel_solve_warp(double* __restrict__ Ls, const 
   }
 }
 
-// Rank-32 trailing update of the columns beyond panel p (all 8 warps): C -= X_panel L_panel^T on the
-// inverse rows (rows < c0 + 32, strict-upper region) and on the lower part of the L rows.  Work
-// unit = 16 rows x 32 columns (2 x 4 DMMA tiles, K = 32), dealt round-robin to the warps.
+// Rank-32 trailing update with the results of panel p: C -= X_panel L_panel^T on the inverse rows
+// (rows < c0 + 32, strict-upper region) and on the lower part of the L rows, for the 32-column blocks
+// cb_lo .. cb_hi.  Work unit = 16 rows x 32 columns (2 x 4 DMMA tiles, K = 32), dealt round-robin to
+// the `nw` warps wfirst .. wfirst + nw - 1.  The caller splits the update in two: the block right
+// behind the panel (needed by the next panel step) by all warps, the blocks beyond it by the three
+// warps that idle during the next panel step.
 __device__ __forceinline__ void rank32_update(double* __restrict__ Ls, const double* __restrict__ rdiag, int p,
-                                              int warp, int gid, int tig) {
+                                              int cb_lo, int cb_hi, int wfirst, int nw, int warp, int gid,
+                                              int tig) {
   const int c0 = PANEL * p;
+  if (warp < wfirst || warp >= wfirst + nw) return;
   int u = 0;
   for (int rb = 0; rb < TILE / 16; ++rb) {
     const int R0 = 16 * rb;
     const bool lrows = R0 >= c0 + PANEL;
     const bool inblk = (R0 >= c0) && !lrows;
-    for (int cb = p + 1; cb < TILE / PANEL; ++cb) {
+    for (int cb = cb_lo; cb <= cb_hi; ++cb) {
       if (lrows && PANEL * cb > R0 + 15) continue;
-      if ((u++ & 7) != warp) continue;
+      if ((u++ % nw) != warp - wfirst) continue;
       const int C0 = PANEL * cb;
       double af[2][8], bf[4][8], cf[2][4][2];
 #pragma unroll
@@ -374,10 +379,15 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
     } else if (warp <= 4) {
       panel_solve_warp(Ls, rdiag, LT, rowL, c0, (warp - 1) * 32 + lane);
       if (prof && lane == 0 && (warp == 1 || warp == 4)) prof[(warp == 1 ? 20 : 24) + p] = clock64();
+    } else if (p >= 1) {
+      // warps 5-7 idle through the panel step: they finish the update of panel p - 1 on the columns
+      // beyond this panel (disjoint from everything the panel step touches)
+      rank32_update(Ls, rdiag, p - 1, p + 1, TILE / PANEL - 1, 5, 3, warp, gid, tig);
     }
     __syncthreads();
     GPAR_PROF(2 + 2 * p);
-    if (p + 1 < TILE / PANEL) rank32_update(Ls, rdiag, p, warp, gid, tig);
+    // the 32 columns right behind the panel: what the next panel step reads
+    if (p + 1 < TILE / PANEL) rank32_update(Ls, rdiag, p, p + 1, p + 1, 0, 8, warp, gid, tig);
     GPAR_PROF(3 + 2 * p);
   }
   __syncthreads();
