@@ -111,6 +111,12 @@ __device__ __forceinline__ void mma_chunk(const GemmStage& st, Acc& acc, int wm,
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    } else if (mask == 0x03u) {  // first row group only (32-row operands: the L^-T sweep of gpar_potri)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dmma884(acc[0][j][0], acc[0][j][1], a[0], b[j]);
+    } else if (mask == 0x02u) {  // ... and right column half only
+#pragma unroll
+      for (int j = 4; j < 8; ++j) dmma884(acc[0][j][0], acc[0][j][1], a[0], b[j]);
     } else if (mask == 0xAAu) {  // right column half only (the common MODE 2 case): straight line
 #pragma unroll
       for (int i = 0; i < 4; ++i)
