@@ -65,8 +65,9 @@ __device__ __forceinline__ void load_chunk(GemmStage& st, const double* __restri
 // triangular tiles load all four SM sub-partitions evenly) and the columns wn*64 + j*8.
 // MODE 0: full tile.  MODE 1: lower-triangular OUTPUT (SYRK on a diagonal tile): 8x8 sub-tiles
 // strictly above the diagonal are skipped.  MODE 2: lower-triangular B OPERAND (B[c][k] = 0 for
-// k > c, i.e. X Linv^T / X L^T): k-steps that only meet zeros are skipped.  Row groups at or
-// beyond `valid_rows` are skipped in every mode (ragged tiles, the single y row).
+// k > c, i.e. X Linv^T / X L^T): k-chunks that only meet zeros are skipped, and the accumulator
+// columns are PERMUTED (acc_col<true>): every consumer of a MODE 2 result passes PERM = true.  Row
+// groups at or beyond `valid_rows` are skipped in every mode (ragged tiles, the single y row).
 __device__ __forceinline__ int acc_row(int wm, int i) { return (4 * i + wm) * 8; }
 
 // Block mask of a warp for one task: bit (2 i + h) enables the 8 x 32 block made of row group i
@@ -87,16 +88,66 @@ __device__ __forceinline__ unsigned block_mask(int wm, int wn, int valid_rows) {
   return m;
 }
 
-// MODE 2 (lower-triangular B OPERAND, B[c][k] = 0 for k > c: X Linv^T, X L^T): a k-chunk starting
-// at k0 only meets zeros in column half h when k0 > last column of the half -- one uniform test
-// per chunk and half.  Blocks are straight-line groups of 4 DMMAs, so skipping costs one uniform
-// branch per block and k-step instead of one per DMMA.
+// Column of accumulator slot j of n-warp wn.  Standard layout: wn owns the contiguous half
+// wn*64 + j*8.  PERM (used by MODE 2 and everything that consumes its accumulators): the 8-column
+// tiles are dealt alternately, (2 j + wn) * 8 -- with a lower-triangular B operand the K-extent of a
+// column tile grows with its index, so the contiguous split leaves the left warp idle for the second
+// half of the K loop (36 vs 100 block-units) while the alternating split gives both warps of a
+// sub-partition 36 chunk-tiles each.
+template <bool PERM>
+__device__ __forceinline__ int acc_col(int wn, int j) { return PERM ? (2 * j + wn) * 8 : wn * 64 + j * 8; }
+
+// MODE 2 (lower-triangular B OPERAND, B[c][k] = 0 for k > c: X Linv^T, X L^T): the k-chunk starting at
+// k0 only meets zeros in column tile ct = 2 j + wn when k0 > 8 ct + 7, i.e. the active tiles are the
+// suffix j >= J0 of the warp's slots: one uniform switch per chunk selects a straight-line body.
+template <int J0>
+__device__ __forceinline__ void mma_tri_steps(const GemmStage& st, Acc& acc, int wm, int wn, int gid, int tig,
+                                              unsigned rowmask) {
+#pragma unroll
+  for (int kk = 0; kk < BK; kk += 4) {
+    double a[4], b[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = st.a[(acc_row(wm, i) + gid) * LDSM + kk + tig];
+#pragma unroll
+    for (int j = J0; j < 8; ++j) b[j] = st.b[(acc_col<true>(wn, j) + gid) * LDSM + kk + tig];
+    if (rowmask == 0xFu) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = J0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    } else {  // ragged tiles, 32-row operands
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (!(rowmask & (1u << i))) continue;
+#pragma unroll
+        for (int j = J0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    }
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void mma_chunk(const GemmStage& st, Acc& acc, int wm, int wn, int gid, int tig, int k0,
                                           unsigned mask) {
   if (MODE == 2) {
-    if (k0 > wn * 64 + 31) mask &= 0xAAu;   // drop h = 0 blocks (bits 0, 2, 4, 6)
-    if (k0 > wn * 64 + 63) mask = 0;
+    unsigned rowmask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (mask & (3u << (2 * i))) rowmask |= 1u << i;
+    const int t = k0 - 8 * wn - 7;
+    const int j0 = t <= 0 ? 0 : (t + 15) / 16;
+    if (rowmask == 0 || j0 > 7) return;
+    switch (j0) {
+      case 0: mma_tri_steps<0>(st, acc, wm, wn, gid, tig, rowmask); break;
+      case 1: mma_tri_steps<1>(st, acc, wm, wn, gid, tig, rowmask); break;
+      case 2: mma_tri_steps<2>(st, acc, wm, wn, gid, tig, rowmask); break;
+      case 3: mma_tri_steps<3>(st, acc, wm, wn, gid, tig, rowmask); break;
+      case 4: mma_tri_steps<4>(st, acc, wm, wn, gid, tig, rowmask); break;
+      case 5: mma_tri_steps<5>(st, acc, wm, wn, gid, tig, rowmask); break;
+      case 6: mma_tri_steps<6>(st, acc, wm, wn, gid, tig, rowmask); break;
+      default: mma_tri_steps<7>(st, acc, wm, wn, gid, tig, rowmask); break;
+    }
+    return;
   }
   if (mask == 0) return;
 #pragma unroll
@@ -114,14 +165,6 @@ __device__ __forceinline__ void mma_chunk(const GemmStage& st, Acc& acc, int wm,
     } else if (mask == 0x03u) {  // first row group only (32-row operands: the L^-T sweep of gpar_potri)
 #pragma unroll
       for (int j = 0; j < 8; ++j) dmma884(acc[0][j][0], acc[0][j][1], a[0], b[j]);
-    } else if (mask == 0x02u) {  // ... and right column half only
-#pragma unroll
-      for (int j = 4; j < 8; ++j) dmma884(acc[0][j][0], acc[0][j][1], a[0], b[j]);
-    } else if (mask == 0xAAu) {  // right column half only (the common MODE 2 case): straight line
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 4; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -217,9 +260,9 @@ __device__ __forceinline__ void gemm_nt_mainloop(GemmStage* stages, const double
                                                  int K, Acc& acc) {
   gemm_nt_pipe<MODE>(stages, Ap, lda, validA, Bp, ldb, validB, K, acc, [](int) {});
 }
-// Epilogue helpers.  Element (i, j, e) of Acc is C[acc_row(wm, i) + gid][wn*64 + j*8 + 2*tig + e].
+// Epilogue helpers.  Element (i, j, e) of Acc is C[acc_row(wm, i) + gid][acc_col<PERM>(wn, j) + 2*tig + e].
 // mode 0: C = acc;  mode 1: C -= acc.  `lower_diag`: only write col <= row (tile on the diagonal).
-template <int MODE>
+template <int MODE, bool PERM = false>
 __device__ __forceinline__ void store_tile(double* __restrict__ C, int64_t ldc, int rows, int cols, const Acc& acc,
                                            bool lower_diag) {
   const int warp = canonical_warp(), lane = threadIdx.x & 31;
@@ -235,7 +278,7 @@ __device__ __forceinline__ void store_tile(double* __restrict__ C, int64_t ldc, 
     if (MODE == 1) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int c = wn * 64 + j * 8 + 2 * tig;
+        const int c = acc_col<PERM>(wn, j) + 2 * tig;
         const bool ok0 = (r < rows) && (c < cols) && (!lower_diag || c <= r);
         const bool ok1 = (r < rows) && (c + 1 < cols) && (!lower_diag || c + 1 <= r);
         old[j] = make_double2(0.0, 0.0);
@@ -250,7 +293,7 @@ __device__ __forceinline__ void store_tile(double* __restrict__ C, int64_t ldc, 
     if (r >= rows) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = wn * 64 + j * 8 + 2 * tig;
+      const int c = acc_col<PERM>(wn, j) + 2 * tig;
       const bool ok0 = (c < cols) && (!lower_diag || c <= r);
       const bool ok1 = (c + 1 < cols) && (!lower_diag || c + 1 <= r);
       double v0 = acc[i][j][0], v1 = acc[i][j][1];
@@ -270,6 +313,7 @@ __device__ __forceinline__ void store_tile(double* __restrict__ C, int64_t ldc, 
 
 // acc += C2 (a dense tile with leading dimension ldc2, written earlier by store_tile<0> of the
 // same thread layout: every thread re-reads exactly the elements it stored).
+template <bool PERM = false>
 __device__ __forceinline__ void acc_add_tile(Acc& acc, const double* __restrict__ C2, int64_t ldc2, int rows,
                                              int cols) {
   const int warp = canonical_warp(), lane = threadIdx.x & 31;
@@ -280,7 +324,7 @@ __device__ __forceinline__ void acc_add_tile(Acc& acc, const double* __restrict_
     if (r >= rows) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = wn * 64 + j * 8 + 2 * tig;
+      const int c = acc_col<PERM>(wn, j) + 2 * tig;
       if (c < cols) acc[i][j][0] += C2[(int64_t)r * ldc2 + c];
       if (c + 1 < cols) acc[i][j][1] += C2[(int64_t)r * ldc2 + c + 1];
     }

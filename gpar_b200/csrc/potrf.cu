@@ -530,28 +530,29 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t strideA, int kt, 
 // --------------------------------------------------------------------------------------
 // X = T L_kk^-T for one 128-row tile: X0 = T Linv^T; when the diagonal block is flagged
 // ill-conditioned, one refinement step R = T - X0 L_kk^T, X = X0 + R Linv^T (X0 parked in a
-// per-CTA scratch tile) restores backward stability.  On return T holds X and so does `acc`.
+// per-CTA scratch tile) restores backward stability.  On return T holds X and so does `acc` -- in the
+// PERMUTED column layout of MODE 2 (acc_col<true>): consumers pass PERM = true.
 __device__ __forceinline__ void tile_solve(GemmStage* stages, double* __restrict__ T, int64_t ldt, int valid, int kb,
                                            const double* __restrict__ Linv, const double* __restrict__ Lkk,
                                            int64_t ldl, bool refine, double* __restrict__ scratch, Acc& acc) {
   acc_zero(acc);
   gemm_nt_mainloop<2>(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);
   if (!refine) {
-    store_tile<0>(T, ldt, valid, kb, acc, false);
+    store_tile<0, true>(T, ldt, valid, kb, acc, false);
     return;
   }
-  store_tile<0>(scratch, TILE, valid, kb, acc, false);  // X0
+  store_tile<0, true>(scratch, TILE, valid, kb, acc, false);  // X0
   __threadfence();
   __syncthreads();
   acc_zero(acc);
   gemm_nt_mainloop<2>(stages, scratch, TILE, valid, Lkk, ldl, kb, kb, acc);  // X0 L_kk^T
-  store_tile<1>(T, ldt, valid, kb, acc, false);                            // T <- R = T - X0 L_kk^T
+  store_tile<1, true>(T, ldt, valid, kb, acc, false);                           // T <- R = T - X0 L_kk^T
   __threadfence();
   __syncthreads();
   acc_zero(acc);
   gemm_nt_mainloop<2>(stages, T, ldt, valid, Linv, TILE, kb, kb, acc);  // R Linv^T
-  acc_add_tile(acc, scratch, TILE, valid, kb);                         // + X0 (each thread re-reads its own stores)
-  store_tile<0>(T, ldt, valid, kb, acc, false);
+  acc_add_tile<true>(acc, scratch, TILE, valid, kb);                         // + X0 (each thread re-reads its own stores)
+  store_tile<0, true>(T, ldt, valid, kb, acc, false);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -772,7 +773,7 @@ __device__ __forceinline__ void gemm_nt_mainloop_dep(GemmStage* stages, const do
     if (readyB != readyA) wait_ready(readyB + kt, sys);
   });
 }
-// X (accumulator layout) -> shared operand tile Xs[128][DLD].
+// X (accumulator layout of tile_solve: permuted columns) -> shared operand tile Xs[128][DLD].
 __device__ __forceinline__ void acc_to_smem(double* __restrict__ Xs, const Acc& acc) {
   const int warp = canonical_warp(), lane = threadIdx.x & 31;
   const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
@@ -780,7 +781,7 @@ __device__ __forceinline__ void acc_to_smem(double* __restrict__ Xs, const Acc& 
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<double2*>(Xs + (acc_row(wm, i) + gid) * DLD + wn * 64 + j * 8 + 2 * tig) =
+      *reinterpret_cast<double2*>(Xs + (acc_row(wm, i) + gid) * DLD + acc_col<true>(wn, j) + 2 * tig) =
           make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
@@ -1075,14 +1076,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
       // multi-GPU: L_ij goes into the peers' copies of the matrix by NVLink stores straight from the
       // accumulators -- first to the rank that owns the next tile row (+ flags), then to the others
       // (a HEAD defers them until its diagonal tile is out: they are off the critical chain).
-      if (multi) store_tile<0>(peer_ptr(T, p.peers.delta[(p.peers.rank + 1) % p.peers.world]), ldi, valid, kb, acc, false);
+      if (multi) store_tile<0, true>(peer_ptr(T, p.peers.delta[(p.peers.rank + 1) % p.peers.world]), ldi, valid, kb, acc, false);
       if (kind == TASK_HEAD) acc_to_smem(Xs, acc);  // the ring is idle: park X as the SYRK operand
       fence_publish(pe);
       __syncthreads();
       if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe, PEERS_FIRST);
       if (multi && p.peers.world > 2 && kind != TASK_HEAD) {
         for (int pr = 0; pr < p.peers.world; ++pr)
-          if (peer_in_set(pe, pr, PEERS_REST)) store_tile<0>(peer_ptr(T, p.peers.delta[pr]), ldi, valid, kb, acc, false);
+          if (peer_in_set(pe, pr, PEERS_REST)) store_tile<0, true>(peer_ptr(T, p.peers.delta[pr]), ldi, valid, kb, acc, false);
         __threadfence_system();
         __syncthreads();
         if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe, PEERS_REST);
