@@ -430,6 +430,48 @@ extern "C" int gpar_mean_axis0(const double* in, int64_t ns, int64_t n, double* 
   return check_launch("gpar_mean_axis0");
 }
 
+// Two percentiles over the sample axis (regression.py:593-594: np.percentile(samples, q, axis=0), numpy's
+// default "linear" method): for every entry i the order statistics j and j + 1 of in[:, i] are found by
+// rank counting (no scratch, no writes; the S x n block stays in L2) and combined with numpy's _lerp.
+__device__ __forceinline__ double numpy_lerp(double a, double b, double t) {
+  const double d = b - a;
+  return (t >= 0.5) ? b - d * (1.0 - t) : a + d * t;
+}
+
+__global__ void __launch_bounds__(128)
+percentile2_axis0_kernel(const double* __restrict__ in, int64_t ns, int64_t n, int64_t j_lo, double g_lo, int64_t j_hi,
+                         double g_hi, double* __restrict__ out_lo, double* __restrict__ out_hi) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t jl1 = (j_lo + 1 < ns) ? j_lo + 1 : ns - 1, jh1 = (j_hi + 1 < ns) ? j_hi + 1 : ns - 1;
+  double al = 0.0, bl = 0.0, ah = 0.0, bh = 0.0;
+  for (int64_t k = 0; k < ns; ++k) {
+    const double x = in[k * n + i];
+    int64_t rank = 0;
+    for (int64_t l = 0; l < ns; ++l) {
+      const double v = in[l * n + i];
+      rank += (v < x) || (v == x && l < k);
+    }
+    if (rank == j_lo) al = x;
+    if (rank == jl1) bl = x;
+    if (rank == j_hi) ah = x;
+    if (rank == jh1) bh = x;
+  }
+  out_lo[i] = numpy_lerp(al, bl, g_lo);
+  out_hi[i] = numpy_lerp(ah, bh, g_hi);
+}
+
+extern "C" int gpar_percentile2_axis0(const double* in, int64_t ns, int64_t n, int64_t j_lo, double g_lo, int64_t j_hi,
+                                      double g_hi, double* out_lo, double* out_hi, void* stream) {
+  if (n <= 0 || ns <= 0) return 0;
+  if (!in) return -1;
+  if (j_lo < 0 || j_lo >= ns || j_hi < 0 || j_hi >= ns) { set_error("gpar_percentile2_axis0: order statistic out of range"); return -4; }
+  if (!out_lo || !out_hi) return -8;
+  percentile2_axis0_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(in, ns, n, j_lo, g_lo, j_hi,
+                                                                                          g_hi, out_lo, out_hi);
+  return check_launch("gpar_percentile2_axis0");
+}
+
 extern "C" int gpar_transpose_scale(const double* src, int64_t lds, int64_t rows, int64_t cols, const double* scale,
                                     double* dst, int64_t ldd, void* stream) {
   if (rows <= 0 || cols <= 0) return 0;

@@ -241,6 +241,28 @@ class Engine:
         check(rc, "gpar_mean_axis0")
         self.launches += 1
 
+    @staticmethod
+    def numpy_virtual_index(ns, q):
+        """(j, gamma) of np.percentile(..., q) with the default linear method for ns samples, computed with
+        numpy's own floating-point formula (numpy/lib/_function_base_impl.py: virtual index
+        ``(n - 1) * quantiles`` with ``quantiles = q / 100``, gamma = index - floor(index))."""
+        quant = np.true_divide(q, 100.0)
+        vi = (ns - 1) * quant
+        j = int(np.floor(vi))
+        j = min(max(j, 0), ns - 1)
+        return j, float(vi - j)
+
+    def percentile2_axis0(self, inp, ns, n, q_lo, q_hi):
+        """Two percentiles over axis 0 of an (ns, n) device block; returns two device vectors."""
+        lo, hi = self.empty(max(n, 1)), self.empty(max(n, 1))
+        jl, gl = self.numpy_virtual_index(ns, q_lo)
+        jh, gh = self.numpy_virtual_index(ns, q_hi)
+        rc = self.lib.gpar_percentile2_axis0(self.addr(inp), ns, n, jl, gl, jh, gh, self.addr(lo), self.addr(hi),
+                                             self.stream)
+        check(rc, "gpar_percentile2_axis0")
+        self.launches += 1
+        return lo, hi
+
     def fp64_probe(self, mode, iters):
         sink = self.zeros(2)
         flops = C.c_double(0.0)

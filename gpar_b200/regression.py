@@ -209,15 +209,23 @@ class GPARRegressor:
 
     def predict(self, x, w=None, num_samples=100, latent=False, credible_bounds=False, normals=None):
         """Predictive means (and 95% credible bounds) from posterior samples
-        (regression.py:566-597).  With the identity transform and no bounds the
-        sample mean is reduced on the device and only (n*, p) values come back."""
-        if self._untransform_y is _identity and not credible_bounds:
+        (regression.py:566-597).  With the identity transform the sample mean and the credible
+        bounds are reduced on the device and only (n*, p) values come back."""
+        if self._untransform_y is _identity:
+            # identity transform: mean (and the 2.5 / 97.5 percentiles, numpy's linear interpolation) are
+            # reduced on the device; only (n*, p) values come back.  Un-normalisation is a positive affine
+            # map per output, so it commutes with the percentiles.
             dev = self._sample_device(x, w, None, True, num_samples, latent, normals)
             S, ns, p = dev.shape
             eng = self._engine_of(dev)
             out = eng.empty(max(ns * p, 1))
             eng.mean_axis0(dev.reshape(-1), S, ns * p, out)
-            return self._unnormalise_y(out.cpu().numpy().reshape(ns, p))
+            mean = self._unnormalise_y(out.cpu().numpy().reshape(ns, p))
+            if not credible_bounds:
+                return mean
+            lo, hi = eng.percentile2_axis0(dev.reshape(-1), S, ns * p, 2.5, 100 - 2.5)
+            return (mean, self._unnormalise_y(lo.cpu().numpy().reshape(ns, p)),
+                    self._unnormalise_y(hi.cpu().numpy().reshape(ns, p)))
         samples = self.sample(x, w, num_samples=num_samples, latent=latent, posterior=True, normals=normals)
         if num_samples == 1:
             samples = [samples]

@@ -207,6 +207,13 @@ int gpar_mean_identity(const double* y, const double* d, double eps, const doubl
 /* Device-side reductions over the sample axis (regression.py:589): out[i] = mean_s in[s][i]. */
 int gpar_mean_axis0(const double* in, int64_t ns, int64_t n, double* out, void* stream);
 
+/* Two percentiles over the sample axis with numpy's default ("linear") interpolation -- the credible bounds of
+ * regression.py:593-594.  The caller passes, per percentile, the lower order statistic j = floor(h) and the
+ * weight g = h - j of numpy's virtual index h (computed on the host with numpy's own formula, so the weights
+ * are bit-identical); out = lerp(sorted[j], sorted[min(j + 1, ns - 1)], g) per entry.  NaNs are not supported. */
+int gpar_percentile2_axis0(const double* in, int64_t ns, int64_t n, int64_t j_lo, double g_lo, int64_t j_hi,
+                           double g_hi, double* out_lo, double* out_hi, void* stream);
+
 /* Diagnostics: raw fp64 issue-rate probes used by bench.py to state the roofline
  * denominators next to cuBLAS DGEMM.  mode 0 = DMMA m8n8k4, 1 = DFMA.  Returns the
  * number of flops executed per launch through *flops. */

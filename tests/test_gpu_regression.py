@@ -225,3 +225,36 @@ def test_engine_matches_committed_oracle_fixture(name):
     assert abs(lp - gold[f"{name}/logpdf"]) <= 1e-9 * abs(gold[f"{name}/logpdf"])
     ref = gold[f"{name}/mean"]
     assert np.max(np.abs(mean - ref)) <= 1e-6 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("S", [1, 2, 7, 100])
+def test_device_percentiles_match_numpy(S):
+    """gpar_percentile2_axis0 against np.percentile (default linear method, regression.py:593-594)."""
+    from gpar_b200.engine import Engine
+
+    eng = Engine()
+    rng = np.random.default_rng(S)
+    a = rng.standard_normal((S, 333))
+    if S >= 7:
+        a[3] = a[5]  # ties
+    lo, hi = eng.percentile2_axis0(eng.to_device(a).reshape(-1), S, 333, 2.5, 100 - 2.5)
+    assert_allclose(lo.cpu().numpy(), np.percentile(a, 2.5, axis=0), rtol=0, atol=1e-15)
+    assert_allclose(hi.cpu().numpy(), np.percentile(a, 100 - 2.5, axis=0), rtol=0, atol=1e-15)
+
+
+def test_predict_credible_bounds_device_vs_host_path():
+    """predict(credible_bounds=True): device reduction (identity transform) against the reference-style
+    host reduction over the same samples (regression.py:589-595)."""
+    from gpar_b200 import GPARRegressor
+
+    data = bench.make_data(n=200, m=2, p=3, ns=50, S=20, missing=0.1)
+    kw = dict(scale=0.25, noise=0.1, linear=True, nonlinear=True, replace=False, impute=True, normalise_y=True)
+    reg = GPARRegressor(**kw)
+    reg.condition(data["x"], data["y"])
+    normals = {"Z": data["Z"]}
+    mean, lo, hi = reg.predict(data["xs"], num_samples=20, credible_bounds=True, normals=normals)
+    smp = np.stack(reg.sample(data["xs"], num_samples=20, posterior=True, normals=normals))
+    assert_allclose(mean, smp.mean(axis=0), rtol=1e-12, atol=1e-12)
+    assert_allclose(lo, np.percentile(smp, 2.5, axis=0), rtol=1e-12, atol=1e-12)
+    assert_allclose(hi, np.percentile(smp, 97.5, axis=0), rtol=1e-12, atol=1e-12)
+    assert np.all(lo <= hi)
