@@ -86,6 +86,7 @@ SIGNATURES = {
     "gpar_scatter_col": (_int, [_p, _i64, _i64, _p, _p, _i64, _p]),
     "gpar_mean_identity": (_int, [_p, _p, _d, _p, _i64, _p, _p]),
     "gpar_mean_axis0": (_int, [_p, _i64, _i64, _p, _p]),
+    "gpar_sum_axis0_add": (_int, [_p, _i64, _i64, _p, _p]),
     "gpar_percentile2_axis0": (_int, [_p, _i64, _i64, _i64, _d, _i64, _d, _p, _p, _p]),
     "gpar_debug_set_dataflow_prof": (_int, [_p]),
     "gpar_debug_decode_ticket": (_int, [_i64, _i64, _i64, _i64, _i64, C.POINTER(C.c_int32)]),

@@ -430,6 +430,22 @@ extern "C" int gpar_mean_axis0(const double* in, int64_t ns, int64_t n, double* 
   return check_launch("gpar_mean_axis0");
 }
 
+// inout[i] += sum_k in[k][i], k in fixed order: combines the K-slices of a split SYRK deterministically.
+__global__ void sum_axis0_add_kernel(const double* __restrict__ in, int64_t ns, int64_t n, double* __restrict__ inout) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = inout[i];
+  for (int64_t k = 0; k < ns; ++k) s += in[k * n + i];
+  inout[i] = s;
+}
+
+extern "C" int gpar_sum_axis0_add(const double* in, int64_t ns, int64_t n, double* inout, void* stream) {
+  if (n <= 0 || ns <= 0) return 0;
+  if (!in || !inout) return -1;
+  sum_axis0_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, ns, n, inout);
+  return check_launch("gpar_sum_axis0_add");
+}
+
 // Two percentiles over the sample axis (regression.py:593-594: np.percentile(samples, q, axis=0), numpy's
 // default "linear" method): for every entry i the order statistics j and j + 1 of in[:, i] are found by
 // rank counting (no scratch, no writes; the S x n block stays in L2) and combined with numpy's _lerp.

@@ -241,6 +241,11 @@ class Engine:
         check(rc, "gpar_mean_axis0")
         self.launches += 1
 
+    def sum_axis0_add(self, inp, ns, n, inout):
+        rc = self.lib.gpar_sum_axis0_add(self.addr(inp), ns, n, self.addr(inout), self.stream)
+        check(rc, "gpar_sum_axis0_add")
+        self.launches += 1
+
     @staticmethod
     def numpy_virtual_index(ns, q):
         """(j, gamma) of np.percentile(..., q) with the default linear method for ns samples, computed with

@@ -56,9 +56,20 @@ class SparseFactor:
         self.c = eng.zeros(ldz)
         self.terms = eng.zeros(4)  # [row terms, logdet A, |v|^2]
         if n:
-            Ct = eng.empty(M * ldn)
+            # The M x M SYRK has few tiles (10 at M = 512) and a very long K = n: split K into slices run as
+            # one batched SYRK into per-slice partials (zero padding beyond n), summed in slice order.
+            nsl = int(min(16, max(1, n // 2048)))
+            Ks = -(-n // nsl)
+            Ks += Ks & 1
+            ldn = nsl * Ks
+            Ct = eng.zeros(M * ldn) if ldn > n else eng.empty(M * ldn)
             eng.transpose_scale(self.Bt, ldz, n, M, eng.to_device(1.0 / np.sqrt(sig_host)), Ct, ldn)
-            eng.syrk_add(self.JA, ldz, M, Ct, ldn, n)
+            if nsl == 1:
+                eng.syrk_add(self.JA, ldz, M, Ct, ldn, n)
+            else:
+                part = eng.zeros(nsl * M * ldz)
+                eng.syrk_add(part, ldz, M, Ct, ldn, Ks, batch=nsl, strideC=M * ldz, strideW=Ks)
+                eng.sum_axis0_add(part, nsl, M * ldz, self.JA)
             eng.gemv(Ct, ldn, M, n, eng.to_device(y_host / np.sqrt(sig_host)), self.c)
             eng.vfe_rowterms(spec, X.t, X.ld, n, self.Bt, ldz, M, sig, yv, self.terms)
         # v = L_A^-1 c rides along as an appended row

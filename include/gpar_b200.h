@@ -207,6 +207,10 @@ int gpar_mean_identity(const double* y, const double* d, double eps, const doubl
 /* Device-side reductions over the sample axis (regression.py:589): out[i] = mean_s in[s][i]. */
 int gpar_mean_axis0(const double* in, int64_t ns, int64_t n, double* out, void* stream);
 
+/* inout[i] += sum_k in[k][i] (k ascending): combines the K-slices of a split-K SYRK (the M x M matrix
+ * A = I + B Sigma^-1 B^T of the VFE path has few tiles and a very long K) in a fixed order. */
+int gpar_sum_axis0_add(const double* in, int64_t ns, int64_t n, double* inout, void* stream);
+
 /* Two percentiles over the sample axis with numpy's default ("linear") interpolation -- the credible bounds of
  * regression.py:593-594.  The caller passes, per percentile, the lower order statistic j = floor(h) and the
  * weight g = h - j of numpy's virtual index h (computed on the host with numpy's own formula, so the weights
