@@ -82,3 +82,18 @@ def test_regressor_c4_small():
     ref = ora.predict(data["xs"], num_samples=S, normals=O.Normals(queue=queue))
     assert np.max(np.abs(mean - ref)) <= 1e-5 * np.max(np.abs(ref))
     assert reg.x_ind.ndim == 2
+
+
+def test_regressor_sparse_split_k_syrk():
+    """n large enough that A = I + B Sigma^-1 B^T is formed by the split-K SYRK (n // 2048 >= 2 slices,
+    ragged last slice): ELBO against the oracle, rel <= 1e-7."""
+    from gpar_b200 import GPARRegressor
+
+    data = bench.make_data(n=4500, m=2, p=2, ns=20, S=1, missing=0.05)
+    z = np.random.default_rng(4).uniform(0, 1, (40, 2))
+    kw = dict(scale=0.25, noise=0.1, linear=True, linear_scale=10.0, nonlinear=True, nonlinear_scale=1.0,
+              replace=True, impute=True, normalise_y=True, x_ind=z)
+    reg, ora = GPARRegressor(**kw), O.OracleRegressor(**kw)
+    reg.condition(data["x"], data["y"]); ora.condition(data["x"], data["y"])
+    a, b = reg.logpdf(data["x"], data["y"]), ora.logpdf(data["x"], data["y"])
+    assert abs(a - b) <= 1e-7 * abs(b)
