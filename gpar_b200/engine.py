@@ -176,10 +176,11 @@ class Engine:
         self.launches += 1
 
     def vfe_rowterms(self, spec, X, ldx, n, Bt, ldb, M, sigma, y, out, out_off=0):
+        wsr = self.empty(592)  # GPAR_VFE_ROWTERMS_WS
         rc = self.lib.gpar_vfe_rowterms(C.byref(spec), self.addr(X), ldx, n, self.addr(Bt), ldb, M, self.addr(sigma),
-                                        self.addr(y), self.addr(out, out_off), self.stream)
+                                        self.addr(y), self.addr(wsr), self.addr(out, out_off), self.stream)
         check(rc, "gpar_vfe_rowterms")
-        self.launches += 1
+        self.launches += 2
 
     # -- K3 -------------------------------------------------------------------
     def backsolve(self, L, ldl, n, ws, u):

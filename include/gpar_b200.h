@@ -169,8 +169,10 @@ int gpar_gram_grad(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx,
  * with Bt = K_xz L_z^-T (n x M), the trace / normaliser / data terms of the bound. */
 int gpar_transpose_scale(const double* src, int64_t lds, int64_t rows, int64_t cols, const double* scale,
                          double* dst, int64_t ldd, void* stream);
+#define GPAR_VFE_ROWTERMS_WS 592 /* doubles of workspace (one partial sum per CTA, combined in a fixed order) */
 int gpar_vfe_rowterms(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t n, const double* Bt,
-                      int64_t ldb, int64_t M, const double* sigma, const double* y, double* out, void* stream);
+                      int64_t ldb, int64_t M, const double* sigma, const double* y, double* workspace, double* out,
+                      void* stream);
 
 /* K3 -- alpha <- L^-T u (u is read only; `work` is n doubles of scratch);
  * out2[0] = 2 sum log L_ii, out2[1] = ||u||^2.  Normal.logpdf tail / iqf. */
