@@ -228,3 +228,18 @@ def test_dataflow_task_list_covers_every_tile_once_and_orders_dependencies(n, nb
         owners = [tile_row_owner(i, world) for i in range(nt + nbt)]
         assert owners[:4] == [0, 0, 0, 0][: len(owners[:4])]
         assert set(owners) == set(range(min(world, (nt + nbt + 3) // 4)))
+
+
+def test_numpy_virtual_index_reproduces_np_percentile():
+    """Host half of the device credible bounds: (j, gamma) + numpy's _lerp == np.percentile bit for bit."""
+    from gpar_b200.engine import Engine
+
+    rng = np.random.default_rng(0)
+    for ns in (1, 2, 3, 10, 100, 101, 257):
+        a = np.sort(rng.standard_normal(ns))
+        for q in (2.5, 97.5, 50.0, 0.0, 100.0):
+            j, g = Engine.numpy_virtual_index(ns, q)
+            lo, hi = a[j], a[min(j + 1, ns - 1)]
+            d = hi - lo
+            got = hi - d * (1.0 - g) if g >= 0.5 else lo + d * g
+            assert got == np.percentile(a, q), (ns, q)
