@@ -1,11 +1,19 @@
-// K2 / K4 / K5: blocked Cholesky with appended row blocks, triangular solve of row blocks, and
-// the symmetric rank-k downdate -- all on the DMMA GEMM core (gemm_core.cuh).
+// K2 / K4 / K5 / K10: blocked Cholesky with appended row blocks (one GPU or sharded over the GPUs of an
+// NVLink domain), triangular solve of row blocks, symmetric rank-k update, and the inverse from the
+// factor -- all on the DMMA GEMM core (gemm_core.cuh).  Tile = 128.
 //
-// Right-looking tile algorithm, tile = 128:
-//   for k:  diag  : L_kk = chol(A_kk) and Linv_kk = L_kk^-1 (one CTA, latency bound: warp-level
-//                   32x32 factor with shuffle pivots + DMMA block updates out of shared memory)
-//           panel : A_ik <- A_ik Linv_kk^T          (NT GEMM, K = 128)
-//           update: A_ij <- A_ij - A_ik A_jk^T      (NT GEMM, K = 128, lower tiles only)
+// Map of this file:
+//   diag_factor_core        128 x 128 diagonal tile: L_kk, L_kk^-1, conditioning flag (warp-shuffle 32-panels,
+//                           substitution row solves, rank-32 DMMA updates), + peer pushes when sharded
+//   tile_solve              X = T L_kk^-T through the inverse tile (+ one refinement step when flagged)
+//   potrf_dataflow_kernel   the product path: persistent left-looking tile dataflow (ticketed D0 / HEAD / PLAIN /
+//                           PRE tasks, ready flags, split-K tail); <MULTI> adds row-block ownership and in-kernel
+//                           NVLink pushes (gpar_potrf_multi)
+//   gemm_sub_kernel         C -/+= A B^T (SYRK / GEMM, batched; triangular-operand mode for gpar_potri)
+//   trsm_rows_kernel        B <- B L^-T for extra row blocks after the fact
+//   trtri_rows_kernel       L^-T by the same sweep over the identity (gpar_potri)
+//   potrf_diag / trsm_tile  v1 right-looking sweep, three launches per 128 columns (GPAR_POTRF_V1=1; kept as
+//                           the measured baseline of DESIGN.md section 3)
 // Appended rows B (nb x n) ride along as extra row tiles, so B <- B L^-T falls out of the same
 // sweep: with B = y^T this is the forward solve of the log-marginal; with the joint matrix
 // [[K_aa, .], [K_*a, K_**]] the sweep yields L, V^T = K_*a L^-T and chol(K_** - V^T V) at once.
