@@ -930,7 +930,9 @@ struct DfShape {
 __host__ __device__ __forceinline__ int df_split(const DfShape& sh, int g) {
   if (g < 4 * GPAR_SPLIT_MINK) return 1;  // short parts are not worth a read-modify-write of the tile
   const long r = sh.nt + sh.nbt - g;
-  const long W = r * (r - 1) / 2 * sh.batch / sh.world;  // tile tasks left for this rank
+  // (deliberately NOT divided by sh.world: the K-partition of a tile fixes its rounding, and keeping it
+  //  independent of the number of ranks makes the sharded factor bit-identical to the single-GPU one)
+  const long W = r * (r - 1) / 2 * sh.batch;  // tile tasks left
   const long want = (long)sh.grid * GPAR_SPLIT_WANT_X10 / 10;
   if (W >= want) return 1;
   long s = (want + W - 1) / (W > 0 ? W : 1);
