@@ -315,6 +315,7 @@ def main():
             "frac_of_fp64_roofline_end_to_end": (F * K / t_e2e / 1e12) / peaks["dgemm_tflops"],
             "fp64_peaks": peaks,
             "roofline": roof,
+            "roofline_gram": measure_gram_kernel(eng),
             "logpdf": float(lp),
         }
         if not args.no_cpu_baseline:
@@ -411,6 +412,32 @@ def measure_dominant_kernel(eng, peaks):
             "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_DRAM_SOURCE, "launch_ms": avg * 1e3, "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes,
             "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (MEASURED_PEAKS.json has no fp64 entry)",
             "shape": {"n": n, "appended_rows": 1}}
+
+
+def measure_gram_kernel(eng):
+    """Secondary roofline (north_star: "the Gram build's byte roofline"): gram_kernel building the lower
+    triangle of the C3 joint matrix (n = 8424, 4 input columns, EQ + diag) -- HBM-bound on its output.
+    Algorithmic bytes = 8 * n (n + 1) / 2 written + 8 * n * d read; peak = hbm_gbs of MEASURED_PEAKS.json."""
+    import torch
+
+    from gpar_b200.spec import lower_terms
+
+    n, d = 8424, 4
+    spec = lower_terms([dict(type="eq", variance=1.0, cols=list(range(d)), scales=[0.25] * d)])
+    X = torch.rand(n * d, dtype=torch.float64, device=eng.device)
+    dv = torch.full((n,), 0.1, dtype=torch.float64, device=eng.device)
+    J = eng.empty(n * n)
+    _, avg = _time_events(lambda: eng.gram(spec, X, d, n, J, n, diag=dv, lower_only=True), 5)
+    alg_bytes = 8.0 * n * (n + 1) / 2 + 8.0 * n * d
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    if os.path.exists(path):
+        peak, src = float(json.load(open(path)).get("hbm_gbs", peak)), "MEASURED_PEAKS.json hbm_gbs"
+    ach = alg_bytes / avg / 1e9
+    return {"kernel": "gram_kernel (fused EQ Gram + diag, lower tiles, 64 x 64 tiles)", "bound": "hbm", "achieved": ach,
+            "peak": peak, "unit": "GB/s", "frac": ach / peak, "launch_ms": avg * 1e3, "algorithmic_bytes": alg_bytes,
+            "peak_source": src, "shape": {"n": n, "d": d},
+            "note": "one fp64 exp per entry: the fp64 pipe (not HBM) is the nearer bound, see DESIGN.md section 3"}
 
 
 if __name__ == "__main__":
