@@ -76,3 +76,26 @@ def test_sharded_predict_and_sample_gloo_world2(S):
     err_mean, err_smp, shape = q.get()
     assert shape == (S, 9, 2)
     assert err_mean <= 1e-13 and err_smp == 0.0
+
+
+def test_potrf_layout_is_aligned_and_disjoint():
+    """Layout of the peer-mapped buffer of the sharded Cholesky (identical on every rank): regions do not
+    overlap, bases are 16-byte aligned, the leading dimension is even (C ABI requirements)."""
+    import types
+
+    from gpar_b200 import _lib
+    from gpar_b200.dist import potrf_layout, tile_row_owner
+
+    eng = types.SimpleNamespace(lib=_lib.load())
+    for n, nb in ((1, 0), (127, 1), (128, 1), (1000, 130), (8424, 1)):
+        lay = potrf_layout(eng, n, nb)
+        assert lay["ld"] >= n and lay["ld"] % 2 == 0
+        ws_doubles = eng.lib.gpar_potrf_workspace_bytes(n, nb, 1) // 8
+        regions = [(lay["a"], n * lay["ld"]), (lay["b"], max(nb, 0) * lay["ld"]), (lay["ws"], ws_doubles),
+                   (lay["info"], 2)]
+        end = 0
+        for off, size in regions:
+            assert off >= end and off % 2 == 0  # doubles: even offset = 16-byte aligned
+            end = off + size
+        assert lay["bytes"] >= 8 * end
+    assert [tile_row_owner(i, 2) for i in range(10)] == [0, 0, 0, 0, 1, 1, 1, 1, 0, 0]
