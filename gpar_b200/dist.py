@@ -196,6 +196,7 @@ def potrf_layout(eng, n, nb):
     off_ws = off_b + max(nb, 0) * ld
     off_ws += off_ws & 1
     off_info = off_ws + ws_doubles
+    off_info += off_info & 1
     total = off_info + 2
     return dict(ld=ld, a=off_a, b=off_b, ws=off_ws, info=off_info, bytes=8 * total)
 
