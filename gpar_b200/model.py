@@ -341,9 +341,8 @@ class GPAR:
         if self.sparse:
             from .sparse import logpdf_sparse
 
-            if sample_missing:
-                raise NotImplementedError("sample_missing is not supported with inducing points")
-            return logpdf_sparse(self, x, y, w, only_last_layer, return_inputs, x_ind, outputs)
+            return logpdf_sparse(self, x, y, w, only_last_layer, return_inputs, x_ind, outputs,
+                                 sample_missing=sample_missing, normals=normals)
         eng = self.engine
         if not isinstance(y, dict):
             y = np.asarray(y, dtype=np.float64)

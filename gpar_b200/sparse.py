@@ -124,9 +124,11 @@ def _layer(model):
     return layer if isinstance(layer, LayerModel) else layer[0]
 
 
-def _train_step(gpar, layer, xd, zd, y_i, w_i, is_last, blk=None):
+def _train_step(gpar, layer, xd, zd, y_i, w_i, is_last, blk=None, sample_missing=False, normals=None):
     """One layer of the training-side chain (model.py:165-174 / 220-240 with PseudoObs): returns the
-    factor and the inputs of the next layer."""
+    factor and the inputs of the next layer.  ``sample_missing`` (model.py:229-237): the missing rows of
+    this output are filled with one joint draw from the sparse posterior ``(f | obs)(x[missing], noise /
+    w[missing])`` (``normals``: list of host arrays, one per layer with missing rows, consumed here)."""
     eng = gpar.engine
     avail = ~np.isnan(y_i[:, 0])
     idx = np.flatnonzero(avail)
@@ -146,6 +148,16 @@ def _train_step(gpar, layer, xd, zd, y_i, w_i, is_last, blk=None):
     n_i = xd.n
     col = eng.to_device(y_i[:, 0])
     miss = ~avail
+    if sample_missing and miss.any():
+        n_m = int(miss.sum())
+        idx_m = eng.to_device(np.flatnonzero(miss), torch.int64)
+        Xm = xd.copy_rows(idx_m, n_m)
+        z = normals.pop(0) if normals is not None else np.random.standard_normal(n_m)
+        Z = eng.to_device(np.asarray(z, dtype=np.float64).reshape(1, n_m))
+        y_m, _, _ = fac.sample_rows(Xm, eng.to_device(layer.noise / w_i[miss]), Z, 1, 1, n_m)
+        eng.scatter_col(col, 1, 0, idx_m, y_m, n_m)
+        # after the merge every row counts as observed (model.py:237, 292)
+        avail, miss = np.ones(n_i, dtype=bool), np.zeros(n_i, dtype=bool)
     if gpar.impute and gpar.replace:
         need = np.ones(n_i, dtype=bool)
     else:
@@ -169,7 +181,8 @@ def _zd(gpar, x_ind, p):
     return DevMat.from_host(gpar.engine, x_ind, spare=p + 1)
 
 
-def logpdf_sparse(gpar, x, y, w, only_last_layer, return_inputs, x_ind, outputs):
+def logpdf_sparse(gpar, x, y, w, only_last_layer, return_inputs, x_ind, outputs, sample_missing=False,
+                  normals=None):
     eng = gpar.engine
     if not isinstance(y, dict):
         y = np.asarray(y, dtype=np.float64)
@@ -178,13 +191,16 @@ def logpdf_sparse(gpar, x, y, w, only_last_layer, return_inputs, x_ind, outputs)
     xd = gpar._as_devmat(x, spare=p + 1)
     zd = _zd(gpar, gpar.x_ind if x_ind is None else x_ind, p)
     slots = []
-    for is_last, ((y_i, w_i, mask), model) in last(zip(per_output(y, w, keep=gpar.impute), gpar.layers),
-                                                   select=outputs):
+    normals = list(normals) if normals is not None else None
+    for is_last, ((y_i, w_i, mask), model) in last(
+        zip(per_output(y, w, keep=gpar.impute or sample_missing), gpar.layers), select=outputs
+    ):
         xd = xd.take_rows(mask)
         layer = _layer(model)
         if layer.block is not None:
             raise NotImplementedError("logpdf under a sparse posterior is not supported yet")
-        fac, _, xd, zd = _train_step(gpar, layer, xd, zd, y_i, w_i, is_last)
+        fac, _, xd, zd = _train_step(gpar, layer, xd, zd, y_i, w_i, is_last, sample_missing=sample_missing,
+                                     normals=normals)
         if (not only_last_layer) or is_last:
             slots.append((fac.elbo_slot(), fac.n))
     eng.check_infos()

@@ -97,3 +97,37 @@ def test_regressor_sparse_split_k_syrk():
     reg.condition(data["x"], data["y"]); ora.condition(data["x"], data["y"])
     a, b = reg.logpdf(data["x"], data["y"]), ora.logpdf(data["x"], data["y"])
     assert abs(a - b) <= 1e-7 * abs(b)
+
+
+def test_sparse_logpdf_sample_missing_vs_oracle():
+    """logpdf(sample_missing=True) with inducing points (model.py:229-237 on PseudoObs): the missing rows of
+    every non-final output are filled with a joint draw from the sparse posterior; same injected normals as
+    the oracle => same value (rel 1e-6), other normals => another value."""
+    rng = np.random.default_rng(11)
+    n = 60
+    x = rng.uniform(0, 1, (n, 2)); wv = rng.uniform(size=(n, 3)) + 0.5
+    y = rng.standard_normal((n, 3))
+    y[rng.uniform(size=n) < 0.25, 0] = np.nan
+    y[rng.uniform(size=n) < 0.25, 1] = np.nan
+    z_ind = rng.uniform(0, 1, (12, 2))
+    for replace in (False, True):
+        g, o = both(LAYERS, x_ind=z_ind, replace=replace, impute=False)
+        nm = [int(np.isnan(y[:, 0]).sum())]
+        zs = [rng.standard_normal(n) for _ in range(2)]
+        # per_output(keep=True) drops nothing here (every row has some later observation or is kept): the
+        # oracle consumes one normal vector per layer with missing rows, sized by its own missing count
+        a = g.logpdf(x, y, wv, sample_missing=True, normals=[z.copy() for z in zs_for(g, o, x, y, wv, zs)])
+        b = o.logpdf(x, y, wv, sample_missing=True, normals=O.Normals(queue=[z.copy() for z in zs_for(g, o, x, y, wv, zs)]))
+        assert abs(a - b) <= 1e-6 * abs(b), (replace, a, b)
+
+
+def zs_for(g, o, x, y, w, zs):
+    """Normal vectors cut to the number of missing rows each layer will ask for (layers 0 and 1)."""
+    from oracle.gpar_oracle import per_output
+
+    out = []
+    for li, (y_i, w_i, mask) in enumerate(per_output(y, w, keep=True)):
+        if li >= 2:
+            break
+        out.append(zs[li][: int(np.isnan(y_i[:, 0]).sum())])
+    return [z for z in out if len(z) > 0]
