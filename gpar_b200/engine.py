@@ -41,6 +41,7 @@ class Engine:
         self._infos = []  # device `info` words of the factorizations issued since the last check
         self.group, self.shard_min_n = group, int(shard_min_n)
         self._peer_bufs = []  # peer-mapped allocations of the sharded factorisations still alive
+        self._peer_pool = {}  # nbytes -> free peer-mapped allocations (reused by later factorisations)
 
     def sharded(self, n):
         """True if a factorisation of n rows is spread over the ranks of ``self.group``."""
@@ -50,12 +51,32 @@ class Engine:
 
         return dist.is_initialized() and dist.get_world_size(self.group) > 1
 
+    def peer_buffer(self, nbytes):
+        """Peer-mapped buffer of ``nbytes`` for a sharded factorisation: reused from the pool when one of
+        that size is free (cudaMalloc + IPC exchange only happen the first time).  Collective and
+        deterministic: every rank makes the same calls in the same order, so pool positions line up."""
+        from .dist import PeerBuffer
+
+        free = self._peer_pool.setdefault(int(nbytes), [])
+        buf = free.pop() if free else PeerBuffer(self, nbytes, self.group)
+        self._peer_bufs.append(buf)
+        return buf
+
     def free_peer_buffers(self):
-        """Collective: release the peer-mapped buffers of earlier sharded factorisations (their
-        Factor objects become invalid).  Called by GPARRegressor at the start of every public call."""
-        bufs, self._peer_bufs = self._peer_bufs, []
-        for b in bufs:
-            b.close()
+        """Hand the peer-mapped buffers of earlier sharded factorisations back to the pool (their Factor
+        objects become invalid).  Called by GPARRegressor at the start of every public call; local
+        bookkeeping only, but every rank must call it at the same point."""
+        for b in self._peer_bufs:
+            self._peer_pool.setdefault(b.nbytes, []).append(b)
+        self._peer_bufs = []
+
+    def close_peer_buffers(self):
+        """Collective: unmap and free every pooled peer buffer."""
+        self.free_peer_buffers()
+        pool, self._peer_pool = self._peer_pool, {}
+        for bufs in pool.values():
+            for b in bufs:
+                b.close()
 
     def check_infos(self):
         """Read back the pivot status of every factorization issued since the last call (one
@@ -298,12 +319,11 @@ class Factor:
         self._alpha = None
         if eng.sharded(n):
             # multi-GPU: the joint matrix lives in peer-mapped memory, tile rows are dealt to the ranks
-            from .dist import PeerBuffer, potrf_layout, potrf_sharded
+            from .dist import potrf_layout, potrf_sharded
 
             lay = potrf_layout(eng, n, 1)
             assert lay["ld"] == ld
-            buf = PeerBuffer(eng, lay["bytes"], eng.group)
-            eng._peer_bufs.append(buf)
+            buf = eng.peer_buffer(lay["bytes"])
             self.J = buf.view(lay["a"], n * ld)
             self.u = buf.view(lay["b"], ld)
             self.u.zero_()

@@ -186,7 +186,9 @@ def _worker_regressor(rank, world, port, q):
     reg.condition(data["x"], data["y"])
     lp = reg.logpdf(data["x"], data["y"])
     mean = predict_sharded(reg, data["xs"], num_samples=6, normals=normals)
-    reg._release_sharded()
+    lp_again = reg.logpdf(data["x"], data["y"])  # peer buffers come back from the pool
+    assert lp_again == lp
+    reg._engine.close_peer_buffers()
     if rank == 0:
         ref = GPARRegressor(engine=Engine(), **reg_kw)
         ref.condition(data["x"], data["y"])
