@@ -242,3 +242,29 @@ def test_features_kernel_family_runs():
     reg2.sample(x, p=2, normals=O.Normals(rng=np.random.default_rng(0)))
     vs = reg2.get_variables()
     assert "0/input/scales" in vs and "1/input/scales" not in vs
+
+
+def test_vfe_gradient_weights_match_finite_differences():
+    """oracle/vfe_grad.py: d ELBO along random directions of (K_zz, K_zx, k_jj, sigma) equals the weighted sums."""
+    from oracle.vfe_grad import vfe_elbo, vfe_elbo_weights
+
+    rng = np.random.default_rng(3)
+    M, n = 7, 25
+    z = rng.uniform(0, 1, (M, 2)); x = rng.uniform(0, 1, (n, 2))
+    terms = [dict(type="eq", variance=1.2, cols=[0, 1], scales=[0.4, 0.6])]
+    Kzz, Kzx = O.kernel_matrix(terms, z, z), O.kernel_matrix(terms, z, x)
+    kdiag = np.full(n, 1.2)
+    sigma = rng.uniform(0.05, 0.3, n)
+    y = rng.standard_normal(n)
+    G_zx, G_zz, g_kk, g_sigma = vfe_elbo_weights(Kzz, Kzx, kdiag, sigma, y)
+    for trial in range(4):
+        dzz = rng.standard_normal((M, M)); dzz = dzz + dzz.T
+        dzx = rng.standard_normal((M, n))
+        dkk = rng.standard_normal(n)
+        dsg = rng.standard_normal(n) * 0.01
+        h = 1e-6
+        f1 = vfe_elbo(Kzz + h * dzz, Kzx + h * dzx, kdiag + h * dkk, sigma + h * dsg, y)
+        f0 = vfe_elbo(Kzz - h * dzz, Kzx - h * dzx, kdiag - h * dkk, sigma - h * dsg, y)
+        fd = (f1 - f0) / (2 * h)
+        an = np.sum(G_zx * dzx) + np.sum(G_zz * dzz) + g_kk @ dkk + g_sigma @ dsg
+        assert abs(fd - an) <= 1e-5 * max(1.0, abs(fd)), (trial, fd, an)
