@@ -81,7 +81,7 @@ SIGNATURES = {
     "gpar_logdet_quad": (_int, [_p, _i64, _i64, _p, _p, _p]),
     "gpar_gemv": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
     "gpar_gram_gemv": (_int, [_SPEC, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p]),
-    "gpar_sample_affine": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _p]),
+    "gpar_sample_affine": (_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _p, _p]),
     "gpar_gather_rows": (_int, [_p, _i64, _p, _i64, _i64, _p, _i64, _p]),
     "gpar_scatter_col": (_int, [_p, _i64, _i64, _p, _p, _i64, _p]),
     "gpar_mean_identity": (_int, [_p, _p, _d, _p, _i64, _p, _p]),

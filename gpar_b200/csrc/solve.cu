@@ -127,8 +127,9 @@ constexpr int ST_I = 64;  // rows per CTA
 constexpr int ST_S = 16;  // samples per CTA
 __global__ void __launch_bounds__(256)
 sample_affine_kernel(const double* __restrict__ C, int64_t ldc, int64_t n, int64_t strideC,
-                     const double* __restrict__ mean, const double* __restrict__ sd, const double* __restrict__ Z,
-                     const double* __restrict__ Z2, int64_t ns, double* __restrict__ out) {
+                     const double* __restrict__ mean, const double* __restrict__ sd, int64_t strideSd,
+                     const double* __restrict__ Z, const double* __restrict__ Z2, int64_t ns,
+                     double* __restrict__ out) {
   __shared__ double Cs[ST_I][ST_I + 1];
   __shared__ double Zs[ST_S][ST_I];
   const int b = blockIdx.z;
@@ -159,7 +160,7 @@ sample_affine_kernel(const double* __restrict__ C, int64_t ldc, int64_t n, int64
   }
   if (gi < n) {
     const double mu = mean ? mean[(int64_t)b * n + gi] : 0.0;
-    const double sdv = (sd && Z2) ? sd[(int64_t)b * n + gi] : 0.0;
+    const double sdv = (sd && Z2) ? sd[(int64_t)b * strideSd + gi] : 0.0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int64_t gs = s0 + sg * 4 + q;
@@ -402,13 +403,13 @@ extern "C" int gpar_gemv(const double* A, int64_t lda, int64_t m, int64_t n, con
 }
 
 extern "C" int gpar_sample_affine(const double* C, int64_t ldc, int64_t n, int64_t strideC, const double* mean,
-                                  const double* sd, const double* Z, const double* Z2, int64_t ns, int64_t batch,
-                                  double* out, void* stream) {
+                                  const double* sd, int64_t strideSd, const double* Z, const double* Z2, int64_t ns,
+                                  int64_t batch, double* out, void* stream) {
   if (n <= 0 || ns <= 0 || batch <= 0) return 0;
   if (!C || !Z || !out) return -1;
   if (batch > 65535 || (ns + ST_S - 1) / ST_S > 65535) { set_error("gpar_sample_affine: grid too large"); return -9; }
   dim3 grid((unsigned)((n + ST_I - 1) / ST_I), (unsigned)((ns + ST_S - 1) / ST_S), (unsigned)batch);
-  sample_affine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(C, ldc, n, strideC, mean, sd, Z, Z2, ns, out);
+  sample_affine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(C, ldc, n, strideC, mean, sd, strideSd, Z, Z2, ns, out);
   return check_launch("gpar_sample_affine");
 }
 

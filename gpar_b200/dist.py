@@ -45,13 +45,40 @@ def _world(group):
     return dist.get_rank(group), dist.get_world_size(group)
 
 
-def _local_samples(reg, x, w, start, stop, latent, normals, local_sampler):
+def chain_generator(device, start, group=None):
+    """CUDA generator for the chains [start, ...) of this rank.  Ranks of an SPMD program are usually
+    seeded identically (``torch.manual_seed(k)`` everywhere): drawing from the default generator would
+    make every rank sample the SAME chains and the gathered set would hold S / world distinct ones.
+    A base seed is drawn on group rank 0, broadcast, and offset by the first chain index of the rank."""
+    base = torch.zeros(1, dtype=torch.int64, device=device)
+    rank, world = _world(group)
+    if rank == 0:
+        base[0] = int(torch.randint(0, 2 ** 62, (1,)).item())
+    if world > 1:
+        dist.broadcast(base, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(base.item()) + 1000003 * int(start))
+    return gen
+
+
+def _local_samples(reg, x, w, start, stop, latent, normals, local_sampler, group=None):
     """(S_loc, n*, p) tensor of this rank's chains (already un-normalised / un-transformed)."""
-    if stop <= start:
-        return None
     if local_sampler is not None:
+        if stop <= start:
+            return None
         return torch.as_tensor(np.asarray(local_sampler(start, stop)))
-    dev = reg._sample_device(x, w, None, True, stop - start, latent, shard_normals(normals, start, stop))
+    gen = None
+    if normals is None:  # collective: every rank takes part, also one that owns no chain
+        gen = chain_generator(_dev(group) if dist.is_initialized() else torch.device("cuda", torch.cuda.current_device()),
+                              start, group)
+    if stop <= start:
+        eng = getattr(reg, "_engine", None)
+        if eng is not None and eng.group is not None:
+            # a rank without chains still takes part in the sharded factorisations of the conditioning
+            reg._sample_device(x, w, None, True, 1, latent, None, generator=gen)
+        return None
+    dev = reg._sample_device(x, w, None, True, stop - start, latent, shard_normals(normals, start, stop),
+                             generator=gen)
     # un-normalise / un-transform per sample on the host (regression.py:553-562), then back to the device
     smp = dev.cpu().numpy()
     smp = np.stack([reg._untransform_y(reg._unnormalise_y(smp[s])) for s in range(smp.shape[0])])
@@ -64,7 +91,7 @@ def predict_sharded(reg, x, w=None, num_samples=100, latent=False, normals=None,
     the gloo tests to exercise the partition / reduction logic without a GPU)."""
     rank, world = _world(group)
     start, stop = chain_slice(num_samples, rank, world)
-    smp = _local_samples(reg, x, w, start, stop, latent, normals, local_sampler)
+    smp = _local_samples(reg, x, w, start, stop, latent, normals, local_sampler, group)
     if world == 1:
         return smp.double().mean(dim=0).cpu().numpy()
     # shapes are needed on ranks that own no chain
@@ -84,7 +111,7 @@ def sample_sharded(reg, x, w=None, num_samples=1, latent=False, normals=None, gr
     ``num_samples`` samples (list of (n*, p) arrays, chain order preserved)."""
     rank, world = _world(group)
     start, stop = chain_slice(num_samples, rank, world)
-    smp = _local_samples(reg, x, w, start, stop, latent, normals, local_sampler)
+    smp = _local_samples(reg, x, w, start, stop, latent, normals, local_sampler, group)
     if world == 1:
         return [a for a in smp.cpu().numpy()]
     device = smp.device if smp is not None else _dev(group)

@@ -70,6 +70,56 @@ class Engine:
             self._peer_pool.setdefault(b.nbytes, []).append(b)
         self._peer_bufs = []
 
+    def release_peer_buffer(self, buf):
+        """Return ONE peer-mapped buffer to the pool (Factor.release).  SPMD: every rank releases the
+        same factor at the same point of the program, so the pools stay aligned.  Reuse is safe without a
+        device sync here: the next sharded factorisation starts with reset -> synchronize -> barrier."""
+        for k, b in enumerate(self._peer_bufs):
+            if b is buf:
+                del self._peer_bufs[k]
+                self._peer_pool.setdefault(b.nbytes, []).append(b)
+                return
+
+    def free_bytes(self):
+        """Device memory a new allocation can still get: free on the device plus what torch's caching
+        allocator holds but does not use."""
+        free, _ = torch.cuda.mem_get_info(self.device)
+        return int(free + torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device))
+
+    def chain_chunk(self, S, bytes_per_chain, tiles_per_chain=1, frac=0.6):
+        """Number of diverged chains to process per pass (model.py:557-564 runs them one by one; the
+        arithmetic is independent per chain): as many as fit into ``frac`` of the free device memory
+        (or ``GPAR_CHAIN_CHUNK_BYTES``), trimmed so that the row-tile count of a pass fills whole waves
+        of the SMs."""
+        budget = int(os.environ.get("GPAR_CHAIN_CHUNK_BYTES", 0)) or int(frac * self.free_bytes())
+        hi = int(max(1, min(S, budget // max(int(bytes_per_chain), 1))))
+        if hi >= S:
+            return int(S)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        best, best_eff = hi, 0.0
+        for c in range(hi, max(hi * 3 // 4, 1) - 1, -1):
+            t = c * max(int(tiles_per_chain), 1)
+            eff = t / float(-(-t // sms) * sms)
+            if eff > best_eff + 1e-9:
+                best, best_eff = c, eff
+        return int(best)
+
+    def standard_normal_host(self, n):
+        """n standard normals on the host for the ``sample_missing`` draws (model.py:229-237).  With a
+        process group the engine runs SPMD -- every rank must build the same next-layer inputs -- so
+        rank 0 of the group draws and broadcasts."""
+        if self.group is None:
+            return np.random.standard_normal(int(n))
+        import torch.distributed as dist
+
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return np.random.standard_normal(int(n))
+        t = torch.empty(int(n), dtype=F64, device=self.device)
+        if dist.get_rank(self.group) == 0:
+            t.copy_(torch.as_tensor(np.random.standard_normal(int(n))))
+        dist.broadcast(t, src=dist.get_global_rank(self.group, 0), group=self.group)
+        return t.cpu().numpy()
+
     def close_peer_buffers(self):
         """Collective: unmap and free every pooled peer buffer."""
         self.free_peer_buffers()
@@ -232,10 +282,14 @@ class Engine:
         self.launches += 1 if nq > 0 else 0
 
     # -- K7 -------------------------------------------------------------------
-    def sample_affine(self, Cm, ldc, n, Z, out, ns, batch=1, strideC=0, mean=None, sd=None, Z2=None, c_off=0):
+    def sample_affine(self, Cm, ldc, n, Z, out, ns, batch=1, strideC=0, mean=None, sd=None, Z2=None, c_off=0,
+                      strideSd=None):
+        """``strideSd``: distance between the noise-sd vectors of consecutive matrices of the batch
+        (default n; 0 = one vector shared by the whole batch)."""
         rc = self.lib.gpar_sample_affine(self.addr(Cm, c_off), ldc, n, strideC, None if mean is None else self.addr(mean),
-                                         None if sd is None else self.addr(sd), self.addr(Z),
-                                         None if Z2 is None else self.addr(Z2), ns, batch, self.addr(out), self.stream)
+                                         None if sd is None else self.addr(sd), n if strideSd is None else strideSd,
+                                         self.addr(Z), None if Z2 is None else self.addr(Z2), ns, batch,
+                                         self.addr(out), self.stream)
         check(rc, "gpar_sample_affine")
         self.launches += 1
 
@@ -317,13 +371,14 @@ class Factor:
         n = self.n = self.n_obs + self.n_ext
         self.ld = ld = _even(max(n, 2))
         self._alpha = None
+        self._peer_buf = None
         if eng.sharded(n):
             # multi-GPU: the joint matrix lives in peer-mapped memory, tile rows are dealt to the ranks
             from .dist import potrf_layout, potrf_sharded
 
             lay = potrf_layout(eng, n, 1)
             assert lay["ld"] == ld
-            buf = eng.peer_buffer(lay["bytes"])
+            buf = self._peer_buf = eng.peer_buffer(lay["bytes"])
             self.J = buf.view(lay["a"], n * ld)
             self.u = buf.view(lay["b"], ld)
             self.u.zero_()
@@ -343,6 +398,14 @@ class Factor:
             self.ws, self.info = eng.potrf(self.J, ld, n, B=self.u, ldb=ld, nb=1)
         else:
             self.ws, self.info = eng.empty(2), torch.zeros(1, dtype=torch.int32, device=eng.device)
+
+    def release(self):
+        """Drop the factor: a sharded factor hands its peer-mapped buffer back to the engine's pool (the
+        next sharded factorisation reuses it); single-GPU factors just drop their references."""
+        if self._peer_buf is not None:
+            self.eng.release_peer_buffer(self._peer_buf)
+            self._peer_buf = None
+        self.J = self.u = self.ws = None
 
     def logdet_quad(self, out2, out_off, r0, r1):
         """out2[out_off:out_off+2] = (2 sum_{r0<=i<r1} log L_ii, sum u_i^2)."""

@@ -327,6 +327,8 @@ class GPAR:
                     xd = self._update_inputs_dev(xd, y_i, avail, fac)
                 else:
                     xd = xd.with_col(self.engine.to_device(y_i[:, 0]))
+            if fac is not None:
+                fac.release()
         self.engine.check_infos()
         return gpar
 
@@ -388,7 +390,7 @@ class GPAR:
                         grad_out["layer"] = layer
                 if do_sample:
                     n_m = ext.n
-                    z = normals.pop(0) if normals is not None else np.random.standard_normal(n_m)
+                    z = normals.pop(0) if normals is not None else eng.standard_normal_host(n_m)
                     Z = eng.to_device(np.asarray(z, dtype=np.float64).reshape(1, n_m))
                     mean = eng.empty(n_m)
                     fac.ext_mean(mean)
@@ -399,6 +401,8 @@ class GPAR:
                     xd = self._update_inputs_dev(xd, y_i, avail, fac, sampled=sampled)
                 else:
                     xd = xd.with_col(eng.to_device(y_i[:, 0]))
+            if fac is not None:
+                fac.release()
         eng.check_infos()
         if return_inputs:
             return xd, x_ind
@@ -410,7 +414,8 @@ class GPAR:
         return float(total)
 
     # -- sampling -----------------------------------------------------------------
-    def sample(self, x, w, latent=False, num_samples=1, normals=None, train=None, return_device=False):
+    def sample(self, x, w, latent=False, num_samples=1, normals=None, train=None, return_device=False,
+               generator=None):
         """Ancestral samples at ``x`` (model.py:245-277) for ``num_samples`` independent
         chains at once.
 
@@ -418,13 +423,14 @@ class GPAR:
         (S, p, n) and, when ``latent``, ``"Z2"`` (S, p, n) -- the injected standard
         normals in the reference's draw order (layer-major; latent draw first, then
         the noise draw).  ``train=(x, y, w)`` fuses conditioning with sampling: every
-        layer is factored once jointly over [training rows; test rows].
+        layer is factored once jointly over [training rows; test rows].  ``generator``: torch
+        CUDA generator for the device normals (chain sharding gives every rank its own stream).
         Returns an array (S, n, p).
         """
         if self.sparse:
             from .sparse import sample_sparse
 
-            return sample_sparse(self, x, w, latent, num_samples, normals, train, return_device)
+            return sample_sparse(self, x, w, latent, num_samples, normals, train, return_device, generator)
         eng = self.engine
         S = int(num_samples)
         p = len(self.layers)
@@ -432,8 +438,8 @@ class GPAR:
         xs = self._as_devmat(x, spare=p + 1)
         ns = xs.n
         if normals is None:
-            Zall = torch.randn(S, p, ns, dtype=F64, device=eng.device)
-            Z2all = torch.randn(S, p, ns, dtype=F64, device=eng.device) if latent else None
+            Zall = torch.randn(S, p, ns, dtype=F64, device=eng.device, generator=generator)
+            Z2all = torch.randn(S, p, ns, dtype=F64, device=eng.device, generator=generator) if latent else None
         else:
             Zall = eng.to_device(np.asarray(normals["Z"], dtype=np.float64).reshape(S, p, ns))
             Z2all = eng.to_device(np.asarray(normals["Z2"], dtype=np.float64).reshape(S, p, ns)) if latent else None
@@ -469,6 +475,7 @@ class GPAR:
             f_col = eng.empty(max(S * ns, 1))  # recorded sample (latent f or y)
             y_col = f_col
 
+            owned = True  # the factor of this layer is dropped at the end of the iteration
             if shared:
                 # one joint factorisation over [block / training rows; test rows]
                 if train_iter is not None:
@@ -499,6 +506,7 @@ class GPAR:
                         fac = Factor(eng, layer.spec, blk.X.t, blk.X.ld, blk.d, blk.y, blk.n, 0)
                         fac.n_blk, fac.n_a = blk.n, 0
                         blk.factor = fac
+                    owned = False  # cached on the observation block for later calls
                 else:
                     fac = None
                 f_col, y_col = self._chains_layer(layer, fac, xs_all, S, ns, d_s, sd, Zi, Z2i, latent)
@@ -525,36 +533,53 @@ class GPAR:
                         xd = self._update_inputs_dev(xd, y_i, avail, fac_obs)
                     else:
                         xd = xd.with_col(eng.to_device(y_i[:, 0]))
+            if owned and fac_obs is not None:
+                fac_obs.release()
         eng.check_infos()
         if return_device:
             return out.reshape(S, ns, p)
         return out.reshape(S, ns, p).cpu().numpy()
 
     def _chains_layer(self, layer, fac, xs_all, S, ns, d_s, sd, Zi, Z2i, latent):
-        """One layer for S diverged chains: W_s = K_*s,a L^-T (one TRSM over all chains'
-        rows), Sigma_s = K_** - W_s W_s^T (batched SYRK), C_s = chol (batched), draws."""
+        """One layer for S diverged chains (the reference runs them one after the other,
+        regression.py:557-564; their arithmetic is independent): per chain s,
+        W_s = K(x*_s, X_a) L^-T (one TRSM over the rows of all chains of a pass), Sigma_s = K_** - W_s W_s^T
+        (batched SYRK), C_s = chol (batched), draws.  The chains are processed in passes sized from
+        the free device memory (Engine.chain_chunk): at C5 (S = 256, n* = 2048, n = 32768) the
+        cross-covariance of all chains at once would be 137 GB."""
         eng = self.engine
         spec = layer.spec
         N = S * ns
         ldc = _even(max(ns, 2))
-        Cs = eng.empty(S * ns * ldc)
-        eng.gram_batched(spec, xs_all.t, xs_all.ld, ns, ns * xs_all.ld, Cs, ldc, ns * ldc, S, diag=d_s, strideD=0)
+        ldx = xs_all.ld
+        has_obs = fac is not None and fac.n_obs > 0
+        n_a, ld = (fac.n_obs, fac.ld) if has_obs else (0, 0)
         mean_all = eng.zeros(max(N, 1))
-        if fac is not None and fac.n_obs > 0:
-            n_a, ld = fac.n_obs, fac.ld
-            E = eng.empty(N * ld)
-            eng.gram(spec, xs_all.t, xs_all.ld, N, E, ld, Y=fac.X, ldy=fac.ldx, ny=n_a, lower_only=False)
-            eng.trsm_rows(fac.J, ld, n_a, fac.ws, E, ld, N)
-            eng.gemv(E, ld, N, n_a, fac.u, mean_all)
-            eng.syrk_sub(Cs, ldc, ns, E, ld, n_a, batch=S, strideC=ns * ldc, strideW=ns * ld)
-        self._chain_ws, self._chain_info = eng.potrf(Cs, ldc, ns, batch=S, strideA=ns * ldc)
         f_col = eng.empty(max(N, 1))
-        eng.sample_affine(Cs, ldc, ns, Zi, f_col, 1, batch=S, strideC=ns * ldc, mean=mean_all)
-        y_col = f_col
-        if latent:
-            y_col = eng.empty(max(N, 1))
-            sd_all = sd.repeat(S)
-            eng.sample_affine(Cs, ldc, ns, Zi, y_col, 1, batch=S, strideC=ns * ldc, mean=mean_all, sd=sd_all, Z2=Z2i)
+        y_col = eng.empty(max(N, 1)) if latent else f_col
+        tiles = -(-ns // 128)
+        per_chain = 8 * ns * (ldc + ld) + eng.lib.gpar_potrf_workspace_bytes(ns, 0, 2) // 2
+        chunk = eng.chain_chunk(S, per_chain, tiles)
+        for c0 in range(0, S, chunk):
+            B = min(S, c0 + chunk) - c0
+            r0 = c0 * ns
+            Xc = xs_all.t[r0 * ldx:]
+            mean_c = mean_all[r0:]
+            Cs = eng.empty(B * ns * ldc)
+            eng.gram_batched(spec, Xc, ldx, ns, ns * ldx, Cs, ldc, ns * ldc, B, diag=d_s, strideD=0)
+            if has_obs:
+                E = eng.empty(B * ns * ld)
+                eng.gram(spec, Xc, ldx, B * ns, E, ld, Y=fac.X, ldy=fac.ldx, ny=n_a, lower_only=False)
+                eng.trsm_rows(fac.J, ld, n_a, fac.ws, E, ld, B * ns)
+                eng.gemv(E, ld, B * ns, n_a, fac.u, mean_c)
+                eng.syrk_sub(Cs, ldc, ns, E, ld, n_a, batch=B, strideC=ns * ldc, strideW=ns * ld)
+                del E
+            eng.potrf(Cs, ldc, ns, batch=B, strideA=ns * ldc)
+            eng.sample_affine(Cs, ldc, ns, Zi[c0:c0 + B], f_col[r0:], 1, batch=B, strideC=ns * ldc, mean=mean_c)
+            if latent:
+                eng.sample_affine(Cs, ldc, ns, Zi[c0:c0 + B], y_col[r0:], 1, batch=B, strideC=ns * ldc, mean=mean_c,
+                                  sd=sd, Z2=Z2i[c0:c0 + B], strideSd=0)
+            del Cs
         self._chain_means = mean_all
         return f_col, y_col
 

@@ -113,6 +113,10 @@ class GPARRegressor:
             raise NotImplementedError("Greedy search is not implemented yet.")
         y_cached = {k: list(per_output(self.y, self.w, keep=k)) for k in [True, False]}
         iters = int(kw_args.pop("iters", 1000))
+        want_analytic = bool(kw_args.pop("analytic", True))
+        kw_args.pop("trace", None)  # varz option without a scipy counterpart
+        from ._lib import GparError
+
         for pi in range(self.p):
             if fix:
                 gpar = _construct_gpar(self, self.vs, self.m, pi + 1)
@@ -128,9 +132,12 @@ class GPARRegressor:
             # on the device (gpar_potri + gpar_gram_grad) and pushed through the bound transform here.
             # The joint objective (fix=False: inputs depend on earlier layers' hyper-parameters) and
             # inducing-point layers keep finite differences.
-            analytic = fix and self.x_ind is None and kw_args.pop("analytic", True)
+            analytic = fix and self.x_ind is None and want_analytic
 
             def objective(z):
+                # every evaluation builds fresh factors: hand the peer-mapped buffers of the previous
+                # one back to the pool (multi-GPU engines; SPMD-safe, every rank evaluates the same z)
+                self._release_sharded()
                 self.vs.set_latent_vector(names, z)
                 gpar = _construct_gpar(self, self.vs, self.m, pi + 1)
                 g = {} if analytic else None
@@ -140,7 +147,11 @@ class GPARRegressor:
                                            x_ind=fixed_x_ind, grad_out=g)
                     else:
                         val = -gpar.logpdf(self.x, y_cached, None, only_last_layer=False)
-                except Exception:
+                except GparError as e:
+                    # a non-positive pivot is a legitimate "infeasible point" for the line search; anything
+                    # else (ABI misuse, resource limits, unsupported configuration) must surface
+                    if "not positive definite" not in str(e):
+                        raise
                     return (1e300, np.zeros_like(z)) if analytic else 1e300
                 if not np.isfinite(val):
                     return (1e300, np.zeros_like(z)) if analytic else 1e300
@@ -179,7 +190,7 @@ class GPARRegressor:
         if self._engine is not None and self._engine.group is not None:
             self._engine.free_peer_buffers()
 
-    def _sample_device(self, x, w, p, posterior, num_samples, latent, normals):
+    def _sample_device(self, x, w, p, posterior, num_samples, latent, normals, generator=None):
         self._release_sharded()
         x = _uprank(x)
         if posterior and not self.is_conditioned:
@@ -195,9 +206,10 @@ class GPARRegressor:
             # conditioning is fused into the sampling sweep (one joint factor per layer).
             gpar = _construct_gpar(self, self.vs, self.m, self.p)
             return gpar.sample(x, w, latent=latent, num_samples=num_samples, normals=normals,
-                               train=(self.x, self.y, self.w), return_device=True)
+                               train=(self.x, self.y, self.w), return_device=True, generator=generator)
         gpar = _construct_gpar(self, self.vs, x.shape[1], p)
-        return gpar.sample(x, w, latent=latent, num_samples=num_samples, normals=normals, return_device=True)
+        return gpar.sample(x, w, latent=latent, num_samples=num_samples, normals=normals, return_device=True,
+                           generator=generator)
 
     def sample(self, x, w=None, p=None, posterior=False, num_samples=1, latent=False, normals=None):
         """Sample from the prior or posterior (regression.py:508-564).  ``normals``

@@ -91,31 +91,41 @@ class SparseFactor:
         Bs = eng.empty(max(nq, 1) * ldz)
         eng.gram(self.spec, Xq.t, Xq.ld, nq, Bs, ldz, Y=self.Z.t, ldy=self.Z.ld, ny=M, lower_only=False)
         eng.trsm_rows(self.Jz, ldz, M, self.ws_z, Bs, ldz, nq)
-        Ds = Bs.clone()
+        Ds = eng.empty(max(nq, 1) * ldz)
+        eng.gather_rows(Bs, ldz, None, nq, M, Ds, ldz)
         eng.trsm_rows(self.JA, ldz, M, self.ws_A, Ds, ldz, nq)
         return Bs, Ds
 
     def sample_rows(self, Xs, d_s, Z, S, batch, ns, sd=None, Z2=None):
         """Joint draws at ``batch`` row sets of ``ns`` rows each (stacked in Xs): returns
-        (f_col, y_col, mean) with ``S`` draws per set (S = 1 when batch > 1)."""
+        (f_col, y_col, mean) with ``S`` draws per set (S = 1 when batch > 1).  Row sets (diverged
+        chains) are processed in passes sized from the free device memory."""
         eng, ldz, M = self.eng, self.ldz, self.M
         N = batch * ns
         ldc = _even(max(ns, 2))
-        Cs = eng.empty(batch * ns * ldc)
-        eng.gram_batched(self.spec, Xs.t, Xs.ld, ns, ns * Xs.ld, Cs, ldc, ns * ldc, batch, diag=d_s, strideD=0)
-        Bs, Ds = self._rows_to_factors(Xs, N)
-        eng.syrk_sub(Cs, ldc, ns, Bs, ldz, M, batch=batch, strideC=ns * ldc, strideW=ns * ldz)
-        eng.syrk_add(Cs, ldc, ns, Ds, ldz, M, batch=batch, strideC=ns * ldc, strideW=ns * ldz)
-        eng.potrf(Cs, ldc, ns, batch=batch, strideA=ns * ldc)
         mean = eng.empty(max(N, 1))
-        self.mean_at(Xs.t, Xs.ld, N, mean)
         f_col = eng.empty(max(S * N, 1))
-        eng.sample_affine(Cs, ldc, ns, Z, f_col, S, batch=batch, strideC=ns * ldc, mean=mean)
-        y_col = f_col
-        if sd is not None:
-            y_col = eng.empty(max(S * N, 1))
-            eng.sample_affine(Cs, ldc, ns, Z, y_col, S, batch=batch, strideC=ns * ldc, mean=mean,
-                              sd=sd if batch == 1 else sd.repeat(batch), Z2=Z2)
+        y_col = eng.empty(max(S * N, 1)) if sd is not None else f_col
+        per_set = 8 * ns * (ldc + 2 * ldz) + eng.lib.gpar_potrf_workspace_bytes(ns, 0, 2) // 2
+        chunk = eng.chain_chunk(batch, per_set, -(-ns // 128)) if batch > 1 else 1
+        for b0 in range(0, batch, chunk):
+            B = min(batch, b0 + chunk) - b0
+            r0 = b0 * ns
+            Xc = DevMat(eng, Xs.t[r0 * Xs.ld:], B * ns, Xs.d, Xs.ld)
+            Cs = eng.empty(B * ns * ldc)
+            eng.gram_batched(self.spec, Xc.t, Xc.ld, ns, ns * Xc.ld, Cs, ldc, ns * ldc, B, diag=d_s, strideD=0)
+            Bs, Ds = self._rows_to_factors(Xc, B * ns)
+            eng.syrk_sub(Cs, ldc, ns, Bs, ldz, M, batch=B, strideC=ns * ldc, strideW=ns * ldz)
+            eng.syrk_add(Cs, ldc, ns, Ds, ldz, M, batch=B, strideC=ns * ldc, strideW=ns * ldz)
+            eng.potrf(Cs, ldc, ns, batch=B, strideA=ns * ldc)
+            self.mean_at(Xc.t, Xc.ld, B * ns, mean[r0:])
+            # batch == 1: S draws from one matrix; batch > 1: one draw per row set (Z rows b0 .. b0 + B)
+            Zc = Z if batch == 1 else Z[b0:b0 + B]
+            eng.sample_affine(Cs, ldc, ns, Zc, f_col[S * r0:], S, batch=B, strideC=ns * ldc, mean=mean[r0:])
+            if sd is not None:
+                Z2c = Z2 if batch == 1 else Z2[b0:b0 + B]
+                eng.sample_affine(Cs, ldc, ns, Zc, y_col[S * r0:], S, batch=B, strideC=ns * ldc, mean=mean[r0:],
+                                  sd=sd, Z2=Z2c, strideSd=0)
         return f_col, y_col, mean
 
 
@@ -152,7 +162,7 @@ def _train_step(gpar, layer, xd, zd, y_i, w_i, is_last, blk=None, sample_missing
         n_m = int(miss.sum())
         idx_m = eng.to_device(np.flatnonzero(miss), torch.int64)
         Xm = xd.copy_rows(idx_m, n_m)
-        z = normals.pop(0) if normals is not None else np.random.standard_normal(n_m)
+        z = normals.pop(0) if normals is not None else eng.standard_normal_host(n_m)
         Z = eng.to_device(np.asarray(z, dtype=np.float64).reshape(1, n_m))
         y_m, _, _ = fac.sample_rows(Xm, eng.to_device(layer.noise / w_i[miss]), Z, 1, 1, n_m)
         eng.scatter_col(col, 1, 0, idx_m, y_m, n_m)
@@ -230,7 +240,7 @@ def condition_sparse(gpar, out, x, y, w):
     return out
 
 
-def sample_sparse(gpar, x, w, latent, num_samples, normals, train, return_device):
+def sample_sparse(gpar, x, w, latent, num_samples, normals, train, return_device, generator=None):
     """model.py:245-277 with sparse posteriors; same contract as :meth:`GPAR.sample`."""
     eng = gpar.engine
     S = int(num_samples)
@@ -239,8 +249,8 @@ def sample_sparse(gpar, x, w, latent, num_samples, normals, train, return_device
     xs = gpar._as_devmat(x, spare=p + 1)
     ns = xs.n
     if normals is None:
-        Zall = torch.randn(S, p, ns, dtype=F64, device=eng.device)
-        Z2all = torch.randn(S, p, ns, dtype=F64, device=eng.device) if latent else None
+        Zall = torch.randn(S, p, ns, dtype=F64, device=eng.device, generator=generator)
+        Z2all = torch.randn(S, p, ns, dtype=F64, device=eng.device, generator=generator) if latent else None
     else:
         Zall = eng.to_device(np.asarray(normals["Z"], dtype=np.float64).reshape(S, p, ns))
         Z2all = eng.to_device(np.asarray(normals["Z2"], dtype=np.float64).reshape(S, p, ns)) if latent else None

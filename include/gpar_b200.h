@@ -190,10 +190,11 @@ int gpar_gram_gemv(const gpar_kernel_spec_t* spec, const double* Xq, int64_t ldq
 /* K7 -- joint Gaussian draws with injected normals (Normal.sample; model.py:264-270):
  * for b < batch, s < ns:  out[b][s][i] = mean_b[i] + sum_{j<=i} C_b[i][j] Z[b][s][j]
  *                                        (+ sd_b[i] * Z2[b][s][i] when Z2 != NULL).
- * Z/out are (batch*ns) x n row major; mean (stride n) and sd may be NULL. */
+ * Z/out are (batch*ns) x n row major; mean (stride n) and sd (stride strideSd; 0 = one vector shared by
+ * the batch) may be NULL. */
 int gpar_sample_affine(const double* C, int64_t ldc, int64_t n, int64_t strideC, const double* mean,
-                       const double* sd, const double* Z, const double* Z2, int64_t ns, int64_t batch,
-                       double* out, void* stream);
+                       const double* sd, int64_t strideSd, const double* Z, const double* Z2, int64_t ns,
+                       int64_t batch, double* out, void* stream);
 
 /* K9 -- row gather / column scatter used by per_output masks and `_update_inputs`
  * (model.py:165,220,291-322).  idx are int64 row indices (device). */
