@@ -76,7 +76,10 @@ SIGNATURES = {
     "gpar_gram_grad_workspace_bytes": (C.c_size_t, [_i64]),
     "gpar_gram_grad": (_int, [_SPEC, _p, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p]),
     "gpar_transpose_scale": (_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
-    "gpar_vfe_rowterms": (_int, [_SPEC, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p]),
+    "gpar_vfe_rowterms": (_int, [_SPEC, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _p, _p]),
+    "gpar_gemm_nt": (_int, [_p, _i64, _i64, _i64, _p, _i64, _p, _i64, _i64, _int, _p]),
+    "gpar_axpy": (_int, [_i64, _d, _p, _p, _p]),
+    "gpar_untransform": (_int, [_p, _i64, _i64, _p, _p, _int, _p]),
     "gpar_backsolve": (_int, [_p, _i64, _i64, _p, _p, _p, _p, _p]),
     "gpar_logdet_quad": (_int, [_p, _i64, _i64, _p, _p, _p]),
     "gpar_gemv": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),

@@ -1388,6 +1388,26 @@ static int syrk_impl(double* C, int64_t ldc, int64_t n, int64_t strideC, const d
   return check_launch("gpar_syrk_sub");
 }
 
+extern "C" int gpar_gemm_nt(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, int64_t lda,
+                            const double* B, int64_t ldb, int64_t k, int add, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (m <= 0 || n <= 0 || k <= 0) return 0;
+  if (!C || !aligned16(C) || (ldc & 1) || ldc < n) { set_error("gpar_gemm_nt: bad C"); return -1; }
+  if (!A || !aligned16(A) || (lda & 1) || lda < k) { set_error("gpar_gemm_nt: bad A"); return -5; }
+  if (!B || !aligned16(B) || (ldb & 1) || ldb < k) { set_error("gpar_gemm_nt: bad B"); return -7; }
+  const int64_t mt = (m + TILE - 1) / TILE, ntc = (n + TILE - 1) / TILE;
+  if (mt > 65535) { set_error("gpar_gemm_nt: more than 65535 row tiles"); return -3; }
+  set_smem_attrs();
+  SubArgs p;
+  p.C = C; p.ldc = ldc; p.c_rows = m; p.c_cols = n; p.strideC = 0;
+  p.Aop = A; p.lda = lda; p.strideA = 0;
+  p.Bop = B; p.ldb = ldb; p.strideB = 0;
+  p.K = (int)k; p.lower = 0; p.nt_rows1 = (int)mt; p.add = add; p.tri_k = 0;
+  p.C2 = nullptr; p.ldc2 = 0; p.c_rows2 = 0; p.strideC2 = 0; p.Aop2 = nullptr; p.lda2 = 0; p.strideA2 = 0;
+  gemm_sub_kernel<<<dim3((unsigned)ntc, (unsigned)mt, 1), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+  return check_launch("gpar_gemm_nt");
+}
+
 // K10 -- A^-1 from the factor (gradients of the log-marginal): U <- L^-T, Ainv (lower) <- U U^T.
 extern "C" size_t gpar_potri_scratch_bytes(int64_t n) {
   if (n <= 0) return 0;

@@ -232,7 +232,8 @@ transpose_scale_kernel(const double* __restrict__ src, int64_t lds, int64_t rows
 __global__ void __launch_bounds__(1024)
 vfe_rowterms_kernel(const __grid_constant__ gpar_kernel_spec_t spec, const double* __restrict__ X, int64_t ldx,
                     int64_t n, const double* __restrict__ Bt, int64_t ldb, int64_t M,
-                    const double* __restrict__ sigma, const double* __restrict__ y, double* __restrict__ out) {
+                    const double* __restrict__ sigma, const double* __restrict__ y, const double* __restrict__ Pm,
+                    const double* __restrict__ Pp, int64_t ldp, int64_t Mp, double* __restrict__ out) {
   __shared__ double red[32];
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -242,6 +243,11 @@ vfe_rowterms_kernel(const __grid_constant__ gpar_kernel_spec_t spec, const doubl
     const double* b = Bt + j * ldb;
     double ss = 0.0;
     for (int64_t c = lane; c < M; c += 32) ss = fma(b[c], b[c], ss);
+    if (Pm) {  // the prior of the bound is a sparse posterior: k_jj - |Pm_j|^2 + |Pp_j|^2
+      const double* pm = Pm + j * ldp;
+      const double* pp = Pp + j * ldp;
+      for (int64_t c = lane; c < Mp; c += 32) ss += pm[c] * pm[c] - pp[c] * pp[c];
+    }
     ss = warp_sum(ss);
     if (lane == 0) {
       double kjj = 0.0;
@@ -512,15 +518,56 @@ extern "C" int gpar_transpose_scale(const double* src, int64_t lds, int64_t rows
 
 extern "C" int gpar_vfe_rowterms(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t n,
                                  const double* Bt, int64_t ldb, int64_t M, const double* sigma, const double* y,
-                                 double* workspace, double* out, void* stream) {
+                                 const double* Pm, const double* Pp, int64_t ldp, int64_t Mp, double* workspace,
+                                 double* out, void* stream) {
   if (!spec || !out) return -1;
   if (!workspace) { set_error("gpar_vfe_rowterms: workspace of GPAR_VFE_ROWTERMS_WS doubles required"); return -10; }
   // one CTA used to stream the whole n x M block (1.7 ms at n = 16384, M = 512: 40 GB/s); now the rows are
   // spread over the grid and the per-CTA partials are combined in a fixed order
+  if ((Pm == nullptr) != (Pp == nullptr)) { set_error("gpar_vfe_rowterms: Pm and Pp go together"); return -10; }
   vfe_rowterms_kernel<<<GPAR_VFE_ROWTERMS_WS, 256, 0, (cudaStream_t)stream>>>(*spec, X, ldx, n, Bt, ldb, M, sigma, y,
-                                                                             workspace);
+                                                                             Pm, Pp, ldp, Mp, workspace);
   vfe_rowterms_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, GPAR_VFE_ROWTERMS_WS, out);
   return check_launch("gpar_vfe_rowterms");
+}
+
+__global__ void untransform_kernel(double* __restrict__ a, int64_t total, int64_t p, const double* __restrict__ scale,
+                                   const double* __restrict__ shift, int kind) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t j = e % p;
+  double v = a[e];
+  if (scale) v = v * scale[j] + shift[j];  // y * std + mean, rounded like numpy (no fma)
+  if (kind == GPAR_TRANSFORM_LOG) {
+    v = exp(v);
+  } else if (kind == GPAR_TRANSFORM_SQUISH) {
+    const double m = exp(fabs(v)) - 1.0;
+    v = (v > 0.0) ? m : ((v < 0.0) ? -m : 0.0 * v);  // sign(v) * (exp|v| - 1); NaN stays NaN
+  }
+  a[e] = v;
+}
+
+extern "C" int gpar_untransform(double* a, int64_t rows, int64_t p, const double* scale, const double* shift,
+                                int kind, void* stream) {
+  if (rows <= 0 || p <= 0) return 0;
+  if (!a) return -1;
+  if ((scale == nullptr) != (shift == nullptr)) { set_error("gpar_untransform: scale and shift go together"); return -4; }
+  if (kind < 0 || kind > 2) { set_error("gpar_untransform: unknown transform kind"); return -6; }
+  const int64_t total = rows * p;
+  untransform_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, total, p, scale, shift, kind);
+  return check_launch("gpar_untransform");
+}
+
+__global__ void axpy_kernel(int64_t n, double a, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fma(a, x[i], y[i]);
+}
+
+extern "C" int gpar_axpy(int64_t n, double a, const double* x, double* y, void* stream) {
+  if (n <= 0) return 0;
+  if (!x || !y) return -3;
+  axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, a, x, y);
+  return check_launch("gpar_axpy");
 }
 
 extern "C" int gpar_fp64_probe(int mode, int64_t iters, double* sink, double* flops, void* stream) {

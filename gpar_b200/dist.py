@@ -79,7 +79,14 @@ def _local_samples(reg, x, w, start, stop, latent, normals, local_sampler, group
         return None
     dev = reg._sample_device(x, w, None, True, stop - start, latent, shard_normals(normals, start, stop),
                              generator=gen)
-    # un-normalise / un-transform per sample on the host (regression.py:553-562), then back to the device
+    # un-normalise / un-transform per sample (regression.py:553-562): on the device for the transforms it
+    # knows, else through the host callables
+    from .regression import _transform_kind
+
+    kind = _transform_kind(reg._untransform_y)
+    if kind is not None:
+        reg._untransform_device(reg._engine_of(dev), dev, kind)
+        return dev
     smp = dev.cpu().numpy()
     smp = np.stack([reg._untransform_y(reg._unnormalise_y(smp[s])) for s in range(smp.shape[0])])
     return torch.as_tensor(smp, device=dev.device)

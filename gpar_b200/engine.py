@@ -246,10 +246,25 @@ class Engine:
         check(rc, "gpar_transpose_scale")
         self.launches += 1
 
-    def vfe_rowterms(self, spec, X, ldx, n, Bt, ldb, M, sigma, y, out, out_off=0):
+    def gemm_nt(self, Cm, ldc, m, n, A, lda, B, ldb, k, add=False):
+        """C (m x n) -= A B^T (add: +=), A is m x k, B is n x k."""
+        rc = self.lib.gpar_gemm_nt(self.addr(Cm), ldc, m, n, self.addr(A), lda, self.addr(B), ldb, k, int(add),
+                                   self.stream)
+        check(rc, "gpar_gemm_nt")
+        self.launches += 1 if m * n * k > 0 else 0
+        self.flops += 2.0 * m * n * k
+
+    def axpy(self, n, a, x, y):
+        rc = self.lib.gpar_axpy(n, float(a), self.addr(x), self.addr(y), self.stream)
+        check(rc, "gpar_axpy")
+        self.launches += 1 if n > 0 else 0
+
+    def vfe_rowterms(self, spec, X, ldx, n, Bt, ldb, M, sigma, y, out, out_off=0, Pm=None, Pp=None, ldp=0, Mp=0):
         wsr = self.empty(592)  # GPAR_VFE_ROWTERMS_WS
         rc = self.lib.gpar_vfe_rowterms(C.byref(spec), self.addr(X), ldx, n, self.addr(Bt), ldb, M, self.addr(sigma),
-                                        self.addr(y), self.addr(wsr), self.addr(out, out_off), self.stream)
+                                        self.addr(y), None if Pm is None else self.addr(Pm),
+                                        None if Pp is None else self.addr(Pp), ldp, Mp, self.addr(wsr),
+                                        self.addr(out, out_off), self.stream)
         check(rc, "gpar_vfe_rowterms")
         self.launches += 2
 
@@ -311,6 +326,13 @@ class Engine:
                                          self.addr(out, out_off), self.stream)
         check(rc, "gpar_mean_identity")
         self.launches += 1 if n > 0 else 0
+
+    def untransform(self, a, rows, p, scale, shift, kind):
+        """In place: a[r][j] = T^-1(a[r][j] * scale[j] + shift[j]) (kind 0 identity, 1 exp, 2 inverse squish)."""
+        rc = self.lib.gpar_untransform(self.addr(a), rows, p, None if scale is None else self.addr(scale),
+                                       None if shift is None else self.addr(shift), int(kind), self.stream)
+        check(rc, "gpar_untransform")
+        self.launches += 1 if rows * p > 0 else 0
 
     def mean_axis0(self, inp, ns, n, out):
         rc = self.lib.gpar_mean_axis0(self.addr(inp), ns, n, self.addr(out), self.stream)

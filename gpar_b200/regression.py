@@ -23,6 +23,17 @@ def _identity(x):
     return x
 
 
+def _transform_kind(untransform):
+    """Enum tag of an un-transform the device knows (include/gpar_b200.h GPAR_TRANSFORM_*), else None."""
+    if untransform is _identity:
+        return 0
+    if untransform is log_transform[1]:
+        return 1
+    if untransform is squishing_transform[1]:
+        return 2
+    return None
+
+
 def _uprank(a):
     a = np.asarray(a, dtype=np.float64)
     if a.ndim == 0:
@@ -75,6 +86,7 @@ class GPARRegressor:
         self.n = self.m = self.p = None
         self.normalise_y = normalise_y
         self._unnormalise_y, self._normalise_y = _identity, _identity
+        self._norm = None  # (means, stds) per output once conditioned with normalise_y
         self._transform_y, self._untransform_y = transform_y
         self._engine = engine
 
@@ -100,7 +112,10 @@ class GPARRegressor:
             means, stds = np.array(means)[None, :], np.array(stds)[None, :]
             self._normalise_y = lambda y_: (y_ - means) / stds
             self._unnormalise_y = lambda y_: y_ * stds + means
+            self._norm = (means.reshape(-1).copy(), stds.reshape(-1).copy())
             self.y = self._normalise_y(self.y)
+        else:
+            self._unnormalise_y, self._normalise_y, self._norm = _identity, _identity, None
         self.is_conditioned = True
 
     def fit(self, x, y, w=None, greedy=False, fix=True, **kw_args):
@@ -223,21 +238,22 @@ class GPARRegressor:
         """Predictive means (and 95% credible bounds) from posterior samples
         (regression.py:566-597).  With the identity transform the sample mean and the credible
         bounds are reduced on the device and only (n*, p) values come back."""
-        if self._untransform_y is _identity:
-            # identity transform: mean (and the 2.5 / 97.5 percentiles, numpy's linear interpolation) are
-            # reduced on the device; only (n*, p) values come back.  Un-normalisation is a positive affine
-            # map per output, so it commutes with the percentiles.
+        kind = _transform_kind(self._untransform_y)
+        if kind is not None:
+            # identity / log / squishing transforms: every sample is un-normalised and un-transformed on the
+            # device (regression.py:553-554), then the mean and the 2.5 / 97.5 percentiles (numpy's linear
+            # interpolation) are reduced over the S axis there; only (n*, p) values come back.
             dev = self._sample_device(x, w, None, True, num_samples, latent, normals)
             S, ns, p = dev.shape
             eng = self._engine_of(dev)
+            self._untransform_device(eng, dev, kind)
             out = eng.empty(max(ns * p, 1))
             eng.mean_axis0(dev.reshape(-1), S, ns * p, out)
-            mean = self._unnormalise_y(out.cpu().numpy().reshape(ns, p))
+            mean = out.cpu().numpy().reshape(ns, p)
             if not credible_bounds:
                 return mean
             lo, hi = eng.percentile2_axis0(dev.reshape(-1), S, ns * p, 2.5, 100 - 2.5)
-            return (mean, self._unnormalise_y(lo.cpu().numpy().reshape(ns, p)),
-                    self._unnormalise_y(hi.cpu().numpy().reshape(ns, p)))
+            return mean, lo.cpu().numpy().reshape(ns, p), hi.cpu().numpy().reshape(ns, p)
         samples = self.sample(x, w, num_samples=num_samples, latent=latent, posterior=True, normals=normals)
         if num_samples == 1:
             samples = [samples]
@@ -247,6 +263,15 @@ class GPARRegressor:
             uppers = np.percentile(samples, 100 - 2.5, axis=0)
             return mean, lowers, uppers
         return mean
+
+    def _untransform_device(self, eng, dev, kind):
+        """Un-normalise and un-transform (S, n*, p) device samples in place (gpar_untransform)."""
+        S, ns, p = dev.shape
+        scale = shift = None
+        if self._norm is not None:
+            shift, scale = eng.to_device(self._norm[0]), eng.to_device(self._norm[1])
+        if scale is not None or kind != 0:
+            eng.untransform(dev.reshape(-1), S * ns, p, scale, shift, kind)
 
     def _engine_of(self, _):
         from .model import default_engine

@@ -36,23 +36,48 @@ class SparseBlock:
 
 
 class SparseFactor:
-    def __init__(self, eng, spec, Z, X, y_host, sig_host):
-        self.eng, self.spec, self.Z, self.X = eng, spec, Z, X
+    """VFE quantities of one layer.  ``prior``: the :class:`SparseFactor` of the sparse posterior this layer
+    was conditioned on before (``logpdf(posterior=True)``, regression.py:495-499 -> model.py:286-287 with ``f``
+    a posterior GP): the bound is then taken under that posterior, i.e. with
+
+        m~(a)    = K(a, z_t) beta_t
+        k~(a, b) = k(a, b) - P_a P_b^T + Q_a Q_b^T,   P_a = K(a, z_t) L_zt^-T,  Q_a = P_a L_At^-T
+
+    in the place of the zero mean and the prior kernel."""
+
+    def __init__(self, eng, spec, Z, X, y_host, sig_host, prior=None):
+        self.eng, self.spec, self.Z, self.X, self.prior = eng, spec, Z, X, prior
         M, n = Z.n, X.n
         self.M, self.n = M, n
         ldz = self.ldz = _even(max(M, 2))
         sig = eng.to_device(sig_host)
+        Px = Qx = None
+        if prior is not None:
+            Mt, ldt = prior.M, prior.ldz
+            self.Pz, self.Qz = prior._rows_to_factors(Z, M)  # M x Mt
+            if n:
+                Px, Qx = prior._rows_to_factors(X, n)
+                m_x = eng.empty(n)
+                prior.mean_at(X.t, X.ld, n, m_x)
+                y_host = np.asarray(y_host, dtype=np.float64) - m_x.cpu().numpy()  # y - m~(x)
         yv = eng.to_device(y_host)
         # L_z and B^T = K_xz L_z^-T in one sweep
         self.Jz = eng.empty(M * ldz)
         eng.gram(spec, Z.t, Z.ld, M, self.Jz, ldz, lower_only=True)  # + eps I on the diagonal
+        if prior is not None:
+            eng.syrk_sub(self.Jz, ldz, M, self.Pz, ldt, Mt)
+            eng.syrk_add(self.Jz, ldz, M, self.Qz, ldt, Mt)
         self.Bt = eng.empty(max(n, 1) * ldz)
         if n:
             eng.gram(spec, X.t, X.ld, n, self.Bt, ldz, Y=Z.t, ldy=Z.ld, ny=M, lower_only=False)
+            if prior is not None:
+                eng.gemm_nt(self.Bt, ldz, n, M, Px, ldt, self.Pz, ldt, Mt, add=False)
+                eng.gemm_nt(self.Bt, ldz, n, M, Qx, ldt, self.Qz, ldt, Mt, add=True)
         self.ws_z, self.info_z = eng.potrf(self.Jz, ldz, M, B=self.Bt if n else None, ldb=ldz, nb=n)
         # A = I + C^T C with C = diag(sigma^-1/2) B^T, formed as an NT SYRK on C^T (M x n)
         ldn = _even(max(n, 2))
-        self.JA = torch.eye(M, ldz, dtype=F64, device=eng.device).reshape(-1).contiguous()
+        self.JA = eng.zeros(M * ldz)
+        eng.scatter_col(self.JA, ldz + 1, 0, None, eng.to_device(np.ones(M)), M)  # identity: stride ld + 1
         self.c = eng.zeros(ldz)
         self.terms = eng.zeros(4)  # [row terms, logdet A, |v|^2]
         if n:
@@ -71,12 +96,35 @@ class SparseFactor:
                 eng.syrk_add(part, ldz, M, Ct, ldn, Ks, batch=nsl, strideC=M * ldz, strideW=Ks)
                 eng.sum_axis0_add(part, nsl, M * ldz, self.JA)
             eng.gemv(Ct, ldn, M, n, eng.to_device(y_host / np.sqrt(sig_host)), self.c)
-            eng.vfe_rowterms(spec, X.t, X.ld, n, self.Bt, ldz, M, sig, yv, self.terms)
+            if prior is not None:
+                eng.vfe_rowterms(spec, X.t, X.ld, n, self.Bt, ldz, M, sig, yv, self.terms, Pm=Px, Pp=Qx, ldp=ldt,
+                                 Mp=Mt)
+            else:
+                eng.vfe_rowterms(spec, X.t, X.ld, n, self.Bt, ldz, M, sig, yv, self.terms)
         # v = L_A^-1 c rides along as an appended row
         self.ws_A, self.info_A = eng.potrf(self.JA, ldz, M, B=self.c, ldb=ldz, nb=1)
         eng.logdet_quad(self.JA, ldz, M, self.c, self.terms, out_off=1)
         t = eng.backsolve(self.JA, ldz, M, self.ws_A, self.c)
         self.beta = eng.backsolve(self.Jz, ldz, M, self.ws_z, t)
+        if prior is not None:
+            # posterior-of-posterior mean: m~(q) + k~(q, z) beta = K(q, z_t) (beta_t - h1 + h2) + K(q, z) beta with
+            # h1 = L_zt^-T (P_z^T beta), h2 = L_zt^-T L_At^-T (Q_z^T beta)
+            PzT, QzT = eng.empty(Mt * ldz), eng.empty(Mt * ldz)
+            eng.transpose_scale(self.Pz, ldt, M, Mt, None, PzT, ldz)
+            eng.transpose_scale(self.Qz, ldt, M, Mt, None, QzT, ldz)
+            g1, g2 = eng.zeros(ldt), eng.zeros(ldt)
+            eng.gemv(PzT, ldz, Mt, M, self.beta, g1)
+            eng.gemv(QzT, ldz, Mt, M, self.beta, g2)
+            h1 = eng.backsolve(prior.Jz, ldt, Mt, prior.ws_z, g1)
+            h2 = eng.backsolve(prior.Jz, ldt, Mt, prior.ws_z, eng.backsolve(prior.JA, ldt, Mt, prior.ws_A, g2))
+            self.wt = eng.zeros(ldt)
+            eng.axpy(Mt, 1.0, prior.weights_t(), self.wt)
+            eng.axpy(Mt, -1.0, h1, self.wt)
+            eng.axpy(Mt, 1.0, h2, self.wt)
+
+    def weights_t(self):
+        """Weights of K(., z) in this factor's own posterior mean (a prior-level factor: beta)."""
+        return self.beta
 
     def elbo_slot(self):
         """Device triple (row terms, logdet A, |v|^2): ELBO = -1/2 (t0 + t1 - t2)."""
@@ -84,6 +132,10 @@ class SparseFactor:
 
     def mean_at(self, Xq, ldq, nq, out):
         self.eng.gram_gemv(self.spec, Xq, ldq, nq, self.Z.t, self.Z.ld, self.M, self.beta, out)
+        if self.prior is not None and nq > 0:
+            tmp = self.eng.empty(nq)
+            self.eng.gram_gemv(self.spec, Xq, ldq, nq, self.prior.Z.t, self.prior.Z.ld, self.prior.M, self.wt, tmp)
+            self.eng.axpy(nq, 1.0, tmp, out)
 
     def _rows_to_factors(self, Xq, nq):
         """Bs = K_qz L_z^-T and Ds = Bs L_A^-T for nq query rows."""
@@ -134,7 +186,7 @@ def _layer(model):
     return layer if isinstance(layer, LayerModel) else layer[0]
 
 
-def _train_step(gpar, layer, xd, zd, y_i, w_i, is_last, blk=None, sample_missing=False, normals=None):
+def _train_step(gpar, layer, xd, zd, y_i, w_i, is_last, prior=None, sample_missing=False, normals=None):
     """One layer of the training-side chain (model.py:165-174 / 220-240 with PseudoObs): returns the
     factor and the inputs of the next layer.  ``sample_missing`` (model.py:229-237): the missing rows of
     this output are filled with one joint draw from the sparse posterior ``(f | obs)(x[missing], noise /
@@ -145,7 +197,7 @@ def _train_step(gpar, layer, xd, zd, y_i, w_i, is_last, blk=None, sample_missing
     Xa = xd if len(idx) == xd.n else xd.copy_rows(eng.to_device(idx, torch.int64), len(idx))
     y_a = y_i[avail, 0]
     sig = layer.noise / w_i[avail]
-    fac = SparseFactor(eng, layer.spec, zd, Xa, y_a, sig)
+    fac = SparseFactor(eng, layer.spec, zd, Xa, y_a, sig, prior=prior)
     block = SparseBlock(DevMat(eng, zd.t, zd.n, zd.d, zd.ld), DevMat(eng, Xa.t, Xa.n, Xa.d, Xa.ld), y_a, sig)
     block.factor = fac
     if is_last:
@@ -207,10 +259,17 @@ def logpdf_sparse(gpar, x, y, w, only_last_layer, return_inputs, x_ind, outputs,
     ):
         xd = xd.take_rows(mask)
         layer = _layer(model)
+        prior = None
         if layer.block is not None:
-            raise NotImplementedError("logpdf under a sparse posterior is not supported yet")
-        fac, _, xd, zd = _train_step(gpar, layer, xd, zd, y_i, w_i, is_last, sample_missing=sample_missing,
-                                     normals=normals)
+            # the layer is a sparse posterior (model | data): the bound is taken under it (regression.py:495-499)
+            if sample_missing:
+                raise NotImplementedError("sample_missing under a sparse posterior is not supported")
+            blk = layer.block
+            if blk.factor is None:
+                blk.factor = SparseFactor(eng, layer.spec, blk.Z, blk.X, blk.y_host, blk.sig_host)
+            prior = blk.factor
+        fac, _, xd, zd = _train_step(gpar, layer, xd, zd, y_i, w_i, is_last, prior=prior,
+                                     sample_missing=sample_missing, normals=normals)
         if (not only_last_layer) or is_last:
             slots.append((fac.elbo_slot(), fac.n))
     eng.check_infos()

@@ -144,6 +144,12 @@ int gpar_syrk_sub(double* C, int64_t ldc, int64_t n, int64_t strideC, const doub
 int gpar_syrk_add(double* C, int64_t ldc, int64_t n, int64_t strideC, const double* W, int64_t ldw, int64_t k,
                   int64_t strideW, int64_t batch, void* stream);
 
+/* C (m x n) <- C -/+ A B^T with A (m x k), B (n x k), all row major (add != 0: plus).  Rectangular
+ * counterpart of gpar_syrk_sub / gpar_syrk_add: the cross block k~(x, z) = k(x, z) - B_x B_z^T + D_x D_z^T of a
+ * sparse posterior's kernel (logpdf under a conditioned model, regression.py:495-499). */
+int gpar_gemm_nt(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, int64_t lda, const double* B,
+                 int64_t ldb, int64_t k, int add, void* stream);
+
 /* K10 -- gradients of the dense log-marginal for `fit` (regression.py:434-459; the reference differentiates
  * through Gram + Cholesky + solve with torch autograd):  d LML / d theta = sum_ij W_ij dA_ij / d theta,
  * W = 1/2 (alpha alpha^T - A^-1).
@@ -166,13 +172,26 @@ int gpar_gram_grad(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx,
 /* K8 -- VFE (Titsias) helpers for `PseudoObs` (model.py:286-287).
  * gpar_transpose_scale: dst (cols x rows) = (diag(scale) src)^T, scale may be NULL.
  * gpar_vfe_rowterms: out[0] = sum_j (k_jj - ||Bt_j||^2)/sigma_j + log(2 pi sigma_j) + y_j^2/sigma_j
- * with Bt = K_xz L_z^-T (n x M), the trace / normaliser / data terms of the bound. */
+ * with Bt = K_xz L_z^-T (n x M), the trace / normaliser / data terms of the bound.  When the prior of the
+ * bound is itself a sparse posterior, k_jj is its variance k(x_j, x_j) - ||Pm_j||^2 + ||Pp_j||^2 with the row
+ * blocks Pm, Pp (n x Mp, leading dimension ldp; NULL for a prior GP). */
 int gpar_transpose_scale(const double* src, int64_t lds, int64_t rows, int64_t cols, const double* scale,
                          double* dst, int64_t ldd, void* stream);
 #define GPAR_VFE_ROWTERMS_WS 592 /* doubles of workspace (one partial sum per CTA, combined in a fixed order) */
 int gpar_vfe_rowterms(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t n, const double* Bt,
-                      int64_t ldb, int64_t M, const double* sigma, const double* y, double* workspace, double* out,
-                      void* stream);
+                      int64_t ldb, int64_t M, const double* sigma, const double* y, const double* Pm,
+                      const double* Pp, int64_t ldp, int64_t Mp, double* workspace, double* out, void* stream);
+/* Output transforms on the device (regression.py:22-28, 553-554): every sample is un-normalised and
+ * un-transformed BEFORE the S-axis reduction (quirk Q8: mean of exp, not exp of mean).  a is (rows x p) row
+ * major, in place: a[r][j] = T^-1(a[r][j] * scale[j] + shift[j]); scale / shift may be NULL (no normalisation).
+ * kind: 0 identity, 1 log_transform (T^-1 = exp), 2 squishing_transform (T^-1 = sign(v) (exp|v| - 1)). */
+#define GPAR_TRANSFORM_IDENTITY 0
+#define GPAR_TRANSFORM_LOG 1
+#define GPAR_TRANSFORM_SQUISH 2
+int gpar_untransform(double* a, int64_t rows, int64_t p, const double* scale, const double* shift, int kind,
+                     void* stream);
+/* y <- y + a x (n doubles): combines weight vectors of nested posteriors on the device. */
+int gpar_axpy(int64_t n, double a, const double* x, double* y, void* stream);
 
 /* K3 -- alpha <- L^-T u (u is read only; `work` is n doubles of scratch);
  * out2[0] = 2 sum log L_ii, out2[1] = ||u||^2.  Normal.logpdf tail / iqf. */

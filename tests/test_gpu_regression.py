@@ -258,3 +258,49 @@ def test_predict_credible_bounds_device_vs_host_path():
     assert_allclose(lo, np.percentile(smp, 2.5, axis=0), rtol=1e-12, atol=1e-12)
     assert_allclose(hi, np.percentile(smp, 97.5, axis=0), rtol=1e-12, atol=1e-12)
     assert np.all(lo <= hi)
+
+
+def test_c3_chain_parity_n2048_live_oracle():
+    """The C3 configuration itself (p = 8 layers, EQ + linear + nonlinear, markov = 2, replace + impute, 10 %
+    missing) at n = 2048 -- 16-tile factorizations with HEAD / PRE / PLAIN tasks and the appended y row -- against
+    the live oracle (a few seconds): logpdf rel <= 1e-9, predictive means with shared normals rel <= 1e-5
+    (north_star tolerance), per-sample values rel <= 1e-6."""
+    data_kw, reg_kw = bench.CONFIGS["c3"]
+    kw = {**data_kw, "n": 2048, "ns": 256, "S": 2}
+    data = bench.make_data(**kw)
+    reg, ora = pair(**reg_kw)
+    reg.condition(data["x"], data["y"]); ora.condition(data["x"], data["y"])
+    a, b = reg.logpdf(data["x"], data["y"]), ora.logpdf(data["x"], data["y"])
+    assert abs(a - b) <= 1e-9 * abs(b), (a, b)
+    S, p = kw["S"], kw["p"]
+    smp = np.stack(reg.sample(data["xs"], num_samples=S, posterior=True, normals={"Z": data["Z"]}))
+    ref = np.stack(ora.sample(data["xs"], num_samples=S, posterior=True,
+                              normals=O.Normals(queue=queue_of(data["Z"], None, S, p, False))))
+    assert np.max(np.abs(smp - ref)) <= 1e-6 * np.max(np.abs(ref))
+    mean = reg.predict(data["xs"], num_samples=S, normals={"Z": data["Z"]})
+    assert np.max(np.abs(mean - ref.mean(axis=0))) <= 1e-5 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("which", ["log", "squish"])
+def test_predict_device_transforms_match_host_path(which):
+    """log / squishing transforms (regression.py:22-28): predict() un-normalises and un-transforms every sample
+    on the device (gpar_untransform) before the S-axis reduction (quirk Q8: mean of exp, not exp of mean) --
+    against the reference-style host reduction over the same samples."""
+    from gpar_b200 import GPARRegressor, log_transform, squishing_transform
+
+    tr = log_transform if which == "log" else squishing_transform
+    data = bench.make_data(n=200, m=2, p=3, ns=50, S=20, missing=0.1)
+    y = np.exp(0.3 * data["y"]) if which == "log" else 3.0 * data["y"]
+    kw = dict(scale=0.25, noise=0.1, linear=True, nonlinear=True, replace=False, impute=True, normalise_y=True,
+              transform_y=tr)
+    reg = GPARRegressor(**kw)
+    reg.condition(data["x"], y)
+    normals = {"Z": data["Z"]}
+    mean, lo, hi = reg.predict(data["xs"], num_samples=20, credible_bounds=True, normals=normals)
+    smp = np.stack(reg.sample(data["xs"], num_samples=20, posterior=True, normals=normals))
+    assert_allclose(mean, smp.mean(axis=0), rtol=1e-12, atol=1e-12)
+    assert_allclose(lo, np.percentile(smp, 2.5, axis=0), rtol=1e-12, atol=1e-12)
+    assert_allclose(hi, np.percentile(smp, 97.5, axis=0), rtol=1e-12, atol=1e-12)
+    # Q8: the mean of the un-transformed samples is not the un-transformed mean
+    reg_id = GPARRegressor(**{**kw, "transform_y": (lambda v: v, lambda v: v)})
+    assert np.all(lo <= hi) and np.all(np.isfinite(mean))

@@ -131,3 +131,57 @@ def zs_for(g, o, x, y, w, zs):
             break
         out.append(zs[li][: int(np.isnan(y_i[:, 0]).sum())])
     return [z for z in out if len(z) > 0]
+
+
+def test_regressor_c4_multi_tile_inducing_points():
+    """BASELINE configs[3] with its real number of inducing points (M = 512: four Cholesky tiles of K_zz and of
+    A = I + B Sigma^-1 B^T, multi-tile back-substitutions, split-K SYRK over ~4200 observed rows in two slices, the second ragged) at a
+    size the oracle still handles: ELBO rel <= 1e-7, predictive means rel <= 1e-5, inducing inputs of the next
+    layer (x_ind propagation, model.py:304-305) rel <= 1e-6."""
+    from gpar_b200 import GPARRegressor
+
+    data = bench.make_data(n=4700, m=2, p=3, ns=100, S=2, missing=0.1)
+    z = np.random.default_rng(4).uniform(0, 1, (512, 2))
+    kw = dict(scale=0.25, noise=0.1, linear=True, linear_scale=10.0, nonlinear=True, nonlinear_scale=1.0,
+              replace=True, impute=True, normalise_y=True, x_ind=z)
+    reg, ora = GPARRegressor(**kw), O.OracleRegressor(**kw)
+    reg.condition(data["x"], data["y"]); ora.condition(data["x"], data["y"])
+    a, b = reg.logpdf(data["x"], data["y"]), ora.logpdf(data["x"], data["y"])
+    assert abs(a - b) <= 1e-7 * abs(b), (a, b)
+    S, p = 2, 3
+    mean = reg.predict(data["xs"], num_samples=S, normals={"Z": data["Z"]})
+    queue = [data["Z"][s, i] for s in range(S) for i in range(p)]
+    ref = ora.predict(data["xs"], num_samples=S, normals=O.Normals(queue=queue))
+    assert np.max(np.abs(mean - ref)) <= 1e-5 * np.max(np.abs(ref))
+    # the chain's inputs after the last layer: training rows [x, est_1, est_2] and inducing rows
+    from gpar_b200.regression import _construct_gpar
+
+    g = _construct_gpar(reg, reg.vs, reg.m, reg.p)
+    xd, zd = g.logpdf(reg.x, reg.y, reg.w, return_inputs=True)
+    og = ora._construct_gpar(ora.m, ora.p)
+    xo, zo = og.logpdf(ora.x, ora.y, ora.w, return_inputs=True)
+    assert_allclose(zd.to_host(), zo, rtol=1e-6, atol=1e-8)
+    assert_allclose(xd.to_host(), xo, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("replace,impute", [(False, True), (True, True)])
+def test_logpdf_under_sparse_posterior_vs_oracle(replace, impute):
+    """``GPARRegressor.logpdf(posterior=True)`` with inducing points (regression.py:495-499 -> model.py:148-176,
+    286-287): every layer is a sparse posterior and the new bound is taken under its mean and kernel
+    (k - P P^T + Q Q^T); the chain's inputs / inducing inputs are extended with posterior-of-posterior means.
+    Against the oracle's nested PseudoObs, rel <= 1e-6 (the posterior kernel at the inducing points is formed by
+    cancellation, cond ~ 1e6)."""
+    from gpar_b200 import GPARRegressor
+
+    data = bench.make_data(n=400, m=2, p=3, ns=10, S=1, missing=0.1)
+    new = bench.make_data(n=150, m=2, p=3, ns=10, S=1, missing=0.15, seed=50)
+    z = np.random.default_rng(4).uniform(0, 1, (24, 2))
+    kw = dict(scale=0.25, noise=0.1, linear=True, linear_scale=10.0, nonlinear=True, nonlinear_scale=1.0,
+              replace=replace, impute=impute, normalise_y=True, x_ind=z)
+    reg, ora = GPARRegressor(**kw), O.OracleRegressor(**kw)
+    reg.condition(data["x"], data["y"]); ora.condition(data["x"], data["y"])
+    a = reg.logpdf(new["x"], new["y"], posterior=True)
+    b = ora.logpdf(new["x"], new["y"], posterior=True)
+    assert abs(a - b) <= 1e-6 * abs(b), (a, b)
+    # and it differs from the prior bound (the conditioning matters)
+    assert abs(a - reg.logpdf(new["x"], new["y"])) > 1e-3 * abs(a)
