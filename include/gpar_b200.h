@@ -240,25 +240,10 @@ int gpar_sum_axis0_add(const double* in, int64_t ns, int64_t n, double* inout, v
 int gpar_percentile2_axis0(const double* in, int64_t ns, int64_t n, int64_t j_lo, double g_lo, int64_t j_hi,
                            double g_hi, double* out_lo, double* out_hi, void* stream);
 
-/* Diagnostics: raw fp64 issue-rate probes used by bench.py to state the roofline
- * denominators next to cuBLAS DGEMM.  mode 0 = DMMA m8n8k4, 1 = DFMA.  Returns the
- * number of flops executed per launch through *flops. */
-int gpar_fp64_probe(int mode, int64_t iters, double* sink, double* flops, void* stream);
+/* Diagnostics (probes, profiling hooks, the host decode of the kernel's task list) are NOT part of the drop-in
+ * ABI: they are declared in gpar_b200_debug.h; the raw issue-rate probes live in their own library
+ * (libgpar_b200_debug.so, csrc/debug.cu). */
 
-/* Debug: single-warp dependent-chain latencies in cycles (out: >= 32 doubles). */
-int gpar_debug_latency_probe(double* out, void* stream);
-/* Debug: when non-null, gpar_potrf records globaltimer stamps (24 values) of the tile tasks
- * around column nt/2 of matrix 0 into prof. */
-int gpar_debug_set_dataflow_prof(long long* prof);
-/* Debug / tests: ticket t of the dataflow kernel's task list for an n x n matrix with nb appended rows, decoded on
- * the host by the function the kernel uses, for a launch of `grid` CTAs: out6 = {kind (0 first diagonal tile,
- * 1 head = sub-diagonal solve + diagonal factor of tile row out6[2], 2 plain tile, 3 diagonal pre-update), matrix,
- * tile row, tile column, K-part, number of K-parts of the tile (split-K in the tail of the sweep)}.
- * Returns the number of tickets. */
-int gpar_debug_decode_ticket(int64_t n, int64_t nb, int64_t batch, int64_t grid, int64_t t, int32_t* out6);
-/* Debug: clock64 phase timestamps (21 values) of the diagonal-tile factor on A[0:128, 0:128]. */
-int gpar_debug_diag_profile(double* A, int64_t lda, int64_t n, double* ws, int32_t* info, long long* prof,
-                            void* stream);
 
 #ifdef __cplusplus
 }

@@ -133,6 +133,15 @@ def test_shared_library_exports_header_symbols():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert not any("debug" in n or "probe" in n for n in declared)  # diagnostics live in gpar_b200_debug.h
+    dheader = open(os.path.join(ROOT, "include", "gpar_b200_debug.h")).read()
+    ddecl = set(re.findall(r"\b(gpar_[a-z0-9_]+)\s*\(", dheader))
+    assert ddecl == set(_lib.DEBUG_HOOKS) | set(_lib.DEBUG_PROBES), ddecl
+    for name in _lib.DEBUG_HOOKS:
+        assert hasattr(lib, name)
+    dlib = ctypes.CDLL(_lib.DEBUG_LIB_PATH)
+    for name in _lib.DEBUG_PROBES:
+        assert hasattr(dlib, name) and not hasattr(lib, name)
     assert _lib.load().gpar_abi_version() == 1
     # struct layout must match the header (terms are 32 B, spec = 8 + 8*32 + 96*(4+4+8+8))
     assert ctypes.sizeof(_lib.Term) == 32
