@@ -74,6 +74,9 @@ SIGNATURES = {
     "gpar_potri_scratch_bytes": (C.c_size_t, [_i64]),
     "gpar_potri": (_int, [_p, _i64, _i64, _p, _p, _i64, _p, _i64, _p, _p]),
     "gpar_gram_grad_workspace_bytes": (C.c_size_t, [_i64]),
+    "gpar_gram_wgrad_workspace_bytes": (C.c_size_t, [_i64, _i64]),
+    "gpar_gram_wgrad": (_int, [_SPEC, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _p]),
+    "gpar_row_sqnorm": (_int, [_p, _i64, _i64, _i64, _p, _p]),
     "gpar_gram_grad": (_int, [_SPEC, _p, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p]),
     "gpar_transpose_scale": (_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _p]),
     "gpar_vfe_rowterms": (_int, [_SPEC, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _p, _p]),

@@ -251,19 +251,30 @@ __device__ __forceinline__ double eval_feature_db(const gpar_kernel_spec_t& spec
   return spec.feat_a[f] * x * (op == GPAR_FEAT_SIN ? cos(ang) : -sin(ang));
 }
 
+// RECT (gpar_gram_wgrad): the same sums for a rectangular block k(x_i, y_j), i < n, j < ny, with explicit
+// weights W_ij = ux_i uy_j + sx_i G_ij (every pair counted once; ux / uy / sx / G optional) -- the
+// sum_{m,j} G_zx[m, j] dK(z_m, x_j) and sum G_zz dK(z, z') terms of the VFE bound's gradient.
+struct RectW {
+  const double* Y; int64_t ldy; int64_t ny;
+  const double* G; int64_t ldg;
+  const double* ux; const double* uy; const double* sx;
+};
+
+template <bool RECT>
 __global__ void __launch_bounds__(256)
 gram_grad_kernel(const __grid_constant__ gpar_kernel_spec_t spec, const double* __restrict__ X, int64_t ldx, int64_t n,
                  const double* __restrict__ alpha, const double* __restrict__ Ainv, int64_t lda,
-                 const double* __restrict__ dvec, double* __restrict__ partials) {
+                 const double* __restrict__ dvec, const RectW rw, double* __restrict__ partials) {
   const int bi = blockIdx.y, bj = blockIdx.x;
-  if (bj > bi) return;
+  if (!RECT && bj > bi) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int F = spec.n_feats;
   // layout: [bar 16 B] [raw_x GT*ldx] [raw_y GT*ldx] [fx F*GT] [fy F*GT] [px F*GT] [py F*GT] [ax GT] [ay GT] [accw 8*NP]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* raw_x = reinterpret_cast<double*>(smem_raw + 16);
+  const int64_t ldy = RECT ? rw.ldy : ldx;
   double* raw_y = raw_x + GT * ldx;
-  double* fx = raw_y + GT * ldx;
+  double* fx = raw_y + GT * ldy;
   double* fy = fx + F * GT;
   double* px = fy + F * GT;
   double* py = px + F * GT;
@@ -271,7 +282,7 @@ gram_grad_kernel(const __grid_constant__ gpar_kernel_spec_t spec, const double* 
   double* ay = ax + GT;
   double* accw = ay + GT;
   const int rows_x = static_cast<int>(min64(GT, n - (int64_t)bi * GT));
-  const int rows_y = static_cast<int>(min64(GT, n - (int64_t)bj * GT));
+  const int rows_y = static_cast<int>(min64(GT, (RECT ? rw.ny : n) - (int64_t)bj * GT));
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -280,17 +291,22 @@ gram_grad_kernel(const __grid_constant__ gpar_kernel_spec_t spec, const double* 
   __syncthreads();
   uint32_t parity = 0;
   stage_rows(raw_x, X + (int64_t)bi * GT * ldx, ldx, rows_x, bar, parity);
-  stage_rows(raw_y, X + (int64_t)bj * GT * ldx, ldx, rows_y, bar, parity);
+  stage_rows(raw_y, (RECT ? rw.Y : X) + (int64_t)bj * GT * ldy, ldy, rows_y, bar, parity);
   build_features(spec, fx, raw_x, ldx, rows_x);
-  build_features(spec, fy, raw_y, ldx, rows_y);
+  build_features(spec, fy, raw_y, ldy, rows_y);
   for (int i = threadIdx.x; i < F * GT; i += blockDim.x) {
     const int f = i / GT, r = i % GT;
     px[i] = (r < rows_x) ? eval_feature_db(spec, f, raw_x + r * ldx) : 0.0;
-    py[i] = (r < rows_y) ? eval_feature_db(spec, f, raw_y + r * ldx) : 0.0;
+    py[i] = (r < rows_y) ? eval_feature_db(spec, f, raw_y + r * ldy) : 0.0;
   }
   if (threadIdx.x < GT) {
-    ax[threadIdx.x] = (threadIdx.x < rows_x) ? alpha[(int64_t)bi * GT + threadIdx.x] : 0.0;
-    ay[threadIdx.x] = (threadIdx.x < rows_y) ? alpha[(int64_t)bj * GT + threadIdx.x] : 0.0;
+    if (RECT) {
+      ax[threadIdx.x] = (threadIdx.x < rows_x && rw.ux) ? rw.ux[(int64_t)bi * GT + threadIdx.x] : 0.0;
+      ay[threadIdx.x] = (threadIdx.x < rows_y && rw.uy) ? rw.uy[(int64_t)bj * GT + threadIdx.x] : 0.0;
+    } else {
+      ax[threadIdx.x] = (threadIdx.x < rows_x) ? alpha[(int64_t)bi * GT + threadIdx.x] : 0.0;
+      ay[threadIdx.x] = (threadIdx.x < rows_y) ? alpha[(int64_t)bj * GT + threadIdx.x] : 0.0;
+    }
   }
   __syncthreads();
 
@@ -308,7 +324,12 @@ gram_grad_kernel(const __grid_constant__ gpar_kernel_spec_t spec, const double* 
       const int lc = tx + 16 * c;
       const int64_t gc = (int64_t)bj * GT + lc;
       double w = 0.0;
-      if (lr < rows_x && lc < rows_y && gc <= gr) {
+      if (RECT) {
+        if (lr < rows_x && lc < rows_y) {
+          w = ax[lr] * ay[lc];
+          if (rw.G) w = fma(rw.sx ? rw.sx[gr] : 1.0, __ldcg(rw.G + gr * rw.ldg + gc), w);
+        }
+      } else if (lr < rows_x && lc < rows_y && gc <= gr) {
         w = 0.5 * (ax[lr] * ay[lc] - __ldcg(Ainv + gr * lda + gc));
         if (gc == gr) {
           if (dvec) sdiag = fma(w, dvec[gr], sdiag);
@@ -466,6 +487,17 @@ grad_reduce_kernel(const double* __restrict__ partials, int nb, double* __restri
   if (threadIdx.x == 0) out[q] = v;
 }
 
+// out[q] = sum over ALL tiles of a rectangular pass, row-major tile order (fixed summation order).
+__global__ void __launch_bounds__(256)
+grad_reduce_rect_kernel(const double* __restrict__ partials, int ntile, double* __restrict__ out) {
+  __shared__ double red[32];
+  const int q = blockIdx.x;
+  double v = 0.0;
+  for (int idx = threadIdx.x; idx < ntile; idx += blockDim.x) v += partials[(int64_t)idx * GRAD_NP + q];
+  v = block_sum(v, red);
+  if (threadIdx.x == 0) out[q] = v;
+}
+
 }  // namespace gpar
 
 using namespace gpar;
@@ -544,11 +576,47 @@ extern "C" int gpar_gram_grad(const gpar_kernel_spec_t* spec, const double* X, i
   if (smem > 227 * 1024) { set_error("gpar_gram_grad: ldx/features too large for shared memory (%zu B)", smem); return -3; }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(gram_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gram_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const unsigned nb = (unsigned)((n + GT - 1) / GT);
-  gram_grad_kernel<<<dim3(nb, nb), 256, smem, (cudaStream_t)stream>>>(*spec, X, ldx, n, alpha, Ainv, lda, dvec, workspace);
+  RectW none = {nullptr, 0, 0, nullptr, 0, nullptr, nullptr, nullptr};
+  gram_grad_kernel<false><<<dim3(nb, nb), 256, smem, (cudaStream_t)stream>>>(*spec, X, ldx, n, alpha, Ainv, lda, dvec,
+                                                                            none, workspace);
   grad_reduce_kernel<<<GRAD_NP, 256, 0, (cudaStream_t)stream>>>(workspace, (int)nb, out);
   return check_launch("gpar_gram_grad");
+}
+
+extern "C" size_t gpar_gram_wgrad_workspace_bytes(int64_t nx, int64_t ny) {
+  if (nx <= 0 || ny <= 0) return 0;
+  return (size_t)((nx + GT - 1) / GT) * (size_t)((ny + GT - 1) / GT) * GRAD_NP * sizeof(double);
+}
+
+extern "C" int gpar_gram_wgrad(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t nx,
+                               const double* Y, int64_t ldy, int64_t ny, const double* G, int64_t ldg,
+                               const double* sx, const double* ux, const double* uy, double* workspace, double* out,
+                               void* stream) {
+  if (!spec || spec->n_feats < 0 || spec->n_feats > GPAR_MAX_FEATS || spec->n_terms < 0 ||
+      spec->n_terms > GPAR_MAX_TERMS) { set_error("gpar_gram_wgrad: bad spec"); return -1; }
+  if (!X || ldx <= 0 || !Y || ldy <= 0) { set_error("gpar_gram_wgrad: bad X / Y"); return -2; }
+  if (G && ldg < ny) { set_error("gpar_gram_wgrad: bad G"); return -8; }
+  if ((ux == nullptr) != (uy == nullptr)) { set_error("gpar_gram_wgrad: ux and uy go together"); return -11; }
+  if (!workspace) return -13;
+  if (!out) return -14;
+  if (nx <= 0 || ny <= 0) { cudaMemsetAsync(out, 0, sizeof(double) * GRAD_NP, (cudaStream_t)stream); return 0; }
+  const size_t smem = 16 + sizeof(double) * ((size_t)GT * ldx + (size_t)GT * ldy + 4 * (size_t)spec->n_feats * GT + 2 * GT +
+                                             8 * GRAD_NP);
+  if (smem > 227 * 1024) { set_error("gpar_gram_wgrad: ldx/features too large for shared memory (%zu B)", smem); return -3; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gram_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  const unsigned nbx = (unsigned)((nx + GT - 1) / GT), nby = (unsigned)((ny + GT - 1) / GT);
+  if (nbx > 65535) { set_error("gpar_gram_wgrad: more than 65535 row tiles"); return -4; }
+  RectW rw = {Y, ldy, ny, G, ldg, ux, uy, sx};
+  gram_grad_kernel<true><<<dim3(nby, nbx), 256, smem, (cudaStream_t)stream>>>(*spec, X, ldx, nx, nullptr, nullptr, 0,
+                                                                            nullptr, rw, workspace);
+  grad_reduce_rect_kernel<<<GRAD_NP, 256, 0, (cudaStream_t)stream>>>(workspace, (int)(nbx * nby), out);
+  return check_launch("gpar_gram_wgrad");
 }

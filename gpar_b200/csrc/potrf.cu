@@ -1223,6 +1223,65 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
 #endif
 }
 
+// --------------------------------------------------------------------------------------
+// U = L^-T as a tile dataflow (gpar_potri): tile (r, j), j >= r, of the upper-triangular U is
+//     U_rj = (delta_rj I - sum_{k=r}^{j-1} U_rk L_jk^T) L_jj^-T,
+// i.e. the sweep of trtri_rows_kernel with every tile a task of its own: a persistent grid pulls tickets
+// (column-major: all tiles of column j before column j + 1, longest K first), the K-loop of a tile
+// consumes the tiles U_rk as their ready flags come up, and the chain of a row block shrinks from
+// sum_j (K-loop of j tiles) -- 11.5 ms of 15.9 ms at n = 7424 with one CTA per 32-row block -- to one
+// k-tile + one tile solve per column.  Every dependency has a smaller ticket: deadlock-free.
+// --------------------------------------------------------------------------------------
+struct TrtriArgs {
+  const double* L; int64_t ldl; int64_t n; const double* ws;
+  double* U; int64_t ldu;
+  double* pool;            // gridDim.x scratch tiles (refined solves)
+  int* ticket; int* ready; // ready[r * nt + j]
+  int nt; int total;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trtri_dataflow_kernel(const TrtriArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_task;
+  GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
+  const int tid = threadIdx.x;
+  double* scratch = p.pool + (int64_t)blockIdx.x * TILE * TILE;
+  const double* flags = p.ws + (int64_t)p.nt * TILE * TILE;
+  pipe_init();
+  for (;;) {
+    if (tid == 0) s_task = atomicAdd(p.ticket, 1);
+    __syncthreads();
+    const int t = s_task;
+    __syncthreads();
+    if (t >= p.total) break;
+    int j = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((j + 1) * (j + 2) / 2 <= t) ++j;
+    while (j * (j + 1) / 2 > t) --j;
+    const int r = t - j * (j + 1) / 2;
+    const int valid = static_cast<int>(min64(TILE, p.n - (int64_t)r * TILE));
+    const int kb = static_cast<int>(min64(TILE, p.n - (int64_t)j * TILE));
+    double* Urow = p.U + (int64_t)r * TILE * p.ldu;
+    double* T = Urow + (int64_t)j * TILE;  // holds delta_rj I (set_identity_kernel)
+    const double* Lrow = p.L + (int64_t)j * TILE * p.ldl;
+    if (j > r) {
+      Acc acc;
+      acc_zero(acc);
+      const int* rdy = p.ready + (int64_t)r * p.nt + r;
+      gemm_nt_mainloop_dep<0>(stages, Urow + (int64_t)r * TILE, p.ldu, valid, Lrow + (int64_t)r * TILE, p.ldl, kb,
+                              (j - r) * TILE, acc, rdy, rdy, false, T, p.ldu);
+      store_tile<1>(T, p.ldu, valid, kb, acc, false);
+      __threadfence();
+      __syncthreads();
+    }
+    Acc xacc;
+    tile_solve(stages, T, p.ldu, valid, kb, p.ws + (int64_t)j * TILE * TILE, Lrow + (int64_t)j * TILE, p.ldl,
+               __ldcg(flags + j) != 0.0, scratch, xacc);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release(p.ready + (int64_t)r * p.nt + j, 1);
+  }
+}
+
 static long long* g_df_prof = nullptr;  // debug hook (gpar_debug_set_dataflow_prof)
 
 static void set_smem_attrs() {
@@ -1233,6 +1292,7 @@ static void set_smem_attrs() {
   cudaFuncSetAttribute(gemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
   cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
   cudaFuncSetAttribute(trtri_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
+  cudaFuncSetAttribute(trtri_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES);
   cudaFuncSetAttribute(potrf_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM_BYTES);
   cudaFuncSetAttribute(potrf_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM_BYTES);
   done = true;
@@ -1501,9 +1561,11 @@ extern "C" int gpar_gemm_nt(double* C, int64_t ldc, int64_t m, int64_t n, const 
 }
 
 // K10 -- A^-1 from the factor (gradients of the log-marginal): U <- L^-T, Ainv (lower) <- U U^T.
+// scratch of gpar_potri: [DF_POOL_TILES scratch tiles][ticket (2 ints) + nt * nt ready flags]
 extern "C" size_t gpar_potri_scratch_bytes(int64_t n) {
   if (n <= 0) return 0;
-  return (size_t)((n + TILE - 1) / TILE) * (TILE / TRTRI_ROWS) * TILE * TILE * sizeof(double);
+  const int64_t nt = (n + TILE - 1) / TILE;
+  return (size_t)((int64_t)DF_POOL_TILES * TILE * TILE + (2 + nt * nt + 1) / 2 + 2) * sizeof(double);
 }
 
 extern "C" int gpar_potri(const double* L, int64_t ldl, int64_t n, const double* ws, double* U, int64_t ldu,
@@ -1519,7 +1581,28 @@ extern "C" int gpar_potri(const double* L, int64_t ldl, int64_t n, const double*
   const int64_t total = n * ldu;
   set_identity_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(U, ldu, n);
   const unsigned nt = (unsigned)((n + TILE - 1) / TILE);
-  trtri_rows_kernel<<<nt * (TILE / TRTRI_ROWS), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(L, ldl, n, ws, U, ldu, scratch);
+  static const bool use_rows = (getenv("GPAR_TRTRI_ROWS") != nullptr);  // round-1 sweep, kept as the measured baseline
+  if (use_rows) {
+    if ((size_t)nt * (TILE / TRTRI_ROWS) > (size_t)DF_POOL_TILES) { set_error("gpar_potri: GPAR_TRTRI_ROWS needs n <= %d", DF_POOL_TILES / 4 * TILE); return -9; }
+    trtri_rows_kernel<<<nt * (TILE / TRTRI_ROWS), GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(L, ldl, n, ws, U, ldu, scratch);
+  } else {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    TrtriArgs p;
+    p.L = L; p.ldl = ldl; p.n = n; p.ws = ws; p.U = U; p.ldu = ldu;
+    p.pool = scratch;
+    int* ints = reinterpret_cast<int*>(scratch + (int64_t)DF_POOL_TILES * TILE * TILE);
+    p.ticket = ints; p.ready = ints + 2;
+    p.nt = (int)nt; p.total = (int)(nt * (nt + 1) / 2);
+    cudaMemsetAsync(ints, 0, sizeof(int) * (size_t)(2 + (size_t)nt * nt), stream);
+    int grid = num_sms < DF_POOL_TILES ? num_sms : DF_POOL_TILES;
+    if (grid > p.total) grid = p.total;
+    trtri_dataflow_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+  }
   cudaMemsetAsync(Ainv, 0, sizeof(double) * (size_t)n * lda, stream);
   int rc = syrk_impl(Ainv, lda, n, 0, U, ldu, n, 0, 1, 1, stream_, 1);
   if (rc) return rc;

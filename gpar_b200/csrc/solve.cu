@@ -467,6 +467,26 @@ extern "C" int gpar_untransform(double* a, int64_t rows, int64_t p, const double
   return check_launch("gpar_untransform");
 }
 
+// out[i] = sum_c A[i][c]^2: one warp per row (fixed lane order: deterministic).
+__global__ void __launch_bounds__(256)
+row_sqnorm_kernel(const double* __restrict__ A, int64_t lda, int64_t n, int64_t k, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const double* a = A + row * lda;
+  double s = 0.0;
+  for (int64_t c = lane; c < k; c += 32) s = fma(a[c], a[c], s);
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s;
+}
+
+extern "C" int gpar_row_sqnorm(const double* A, int64_t lda, int64_t n, int64_t k, double* out, void* stream) {
+  if (n <= 0) return 0;
+  if (!A || !out || lda < k) { set_error("gpar_row_sqnorm: bad arguments"); return -1; }
+  row_sqnorm_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(A, lda, n, k, out);
+  return check_launch("gpar_row_sqnorm");
+}
+
 __global__ void axpy_kernel(int64_t n, double a, const double* __restrict__ x, double* __restrict__ y) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = fma(a, x[i], y[i]);

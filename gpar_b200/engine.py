@@ -216,8 +216,9 @@ class Engine:
         self.flops += batch * float(n) ** 2 * k
 
     # -- K10 ------------------------------------------------------------------
-    def potri(self, L, ldl, n, ws):
-        """A^-1 (lower triangle, leading dimension ldl) from the factor L and the workspace of its potrf."""
+    def potri(self, L, ldl, n, ws, return_U=False):
+        """A^-1 (lower triangle, leading dimension ldl) from the factor L and the workspace of its potrf;
+        ``return_U``: also the upper-triangular U = L^-T it is built from."""
         U = self.empty(max(n, 1) * ldl)
         Ainv = self.empty(max(n, 1) * ldl)
         scratch = self.empty(max(self.lib.gpar_potri_scratch_bytes(n) // 8, 2))
@@ -226,7 +227,26 @@ class Engine:
         check(rc, "gpar_potri")
         self.launches += 3
         self.flops += 2.0 * n ** 3 / 3.0
-        return Ainv
+        return (Ainv, U) if return_U else Ainv
+
+    def gram_wgrad(self, spec, X, ldx, nx, Y, ldy, ny, G=None, ldg=0, sx=None, ux=None, uy=None):
+        """Raw chain-rule sums of sum_ij (ux_i uy_j + sx_i G_ij) d k(x_i, y_j) / d spec (device, GRAD_NP)."""
+        wsg = self.empty(max(self.lib.gpar_gram_wgrad_workspace_bytes(nx, ny) // 8, 2))
+        out = self.empty(_lib.GRAD_NP)
+        rc = self.lib.gpar_gram_wgrad(C.byref(spec), self.addr(X), ldx, nx, self.addr(Y), ldy, ny,
+                                      None if G is None else self.addr(G), ldg, None if sx is None else self.addr(sx),
+                                      None if ux is None else self.addr(ux), None if uy is None else self.addr(uy),
+                                      self.addr(wsg), self.addr(out), self.stream)
+        check(rc, "gpar_gram_wgrad")
+        self.launches += 2
+        return out
+
+    def row_sqnorm(self, A, lda, n, k):
+        out = self.empty(max(n, 1))
+        rc = self.lib.gpar_row_sqnorm(self.addr(A), lda, n, k, self.addr(out), self.stream)
+        check(rc, "gpar_row_sqnorm")
+        self.launches += 1 if n > 0 else 0
+        return out
 
     def gram_grad(self, spec, X, ldx, n, alpha, Ainv, lda, dvec=None):
         """Raw chain-rule sums of d LML / d spec (device tensor of _lib.GRAD_NP doubles)."""

@@ -344,7 +344,7 @@ class GPAR:
             from .sparse import logpdf_sparse
 
             return logpdf_sparse(self, x, y, w, only_last_layer, return_inputs, x_ind, outputs,
-                                 sample_missing=sample_missing, normals=normals)
+                                 sample_missing=sample_missing, normals=normals, grad_out=grad_out)
         eng = self.engine
         if not isinstance(y, dict):
             y = np.asarray(y, dtype=np.float64)
@@ -380,14 +380,16 @@ class GPAR:
                 if want_lp:
                     fac.logdet_quad(out2, 2 * li, fac.n_blk, fac.n_obs)
                     counts.append((li, fac.n_a))
-                    if grad_out is not None and is_last and fac.n_a > 0:
+                    if grad_out is not None and (is_last or grad_out.get("every_layer")) and fac.n_a > 0:
                         if fac.n_blk != 0 or fac.n_ext != 0:
                             raise NotImplementedError("gradients are implemented for prior layers only")
                         Ainv = eng.potri(fac.J, fac.ld, fac.n_obs, fac.ws)
                         dvec = eng.to_device(1.0 / w_i[avail])
-                        grad_out["raw"] = eng.gram_grad(layer.spec, fac.X, fac.ldx, fac.n_obs, fac.alpha(), Ainv,
-                                                        fac.ld, dvec)
-                        grad_out["layer"] = layer
+                        raw = eng.gram_grad(layer.spec, fac.X, fac.ldx, fac.n_obs, fac.alpha(), Ainv, fac.ld, dvec)
+                        if grad_out.get("every_layer"):
+                            grad_out.setdefault("per_layer", {})[li] = (raw, layer)
+                        else:
+                            grad_out["raw"], grad_out["layer"] = raw, layer
                 if do_sample:
                     n_m = ext.n
                     z = normals.pop(0) if normals is not None else eng.standard_normal_host(n_m)

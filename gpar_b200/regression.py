@@ -119,10 +119,14 @@ class GPARRegressor:
         self.is_conditioned = True
 
     def fit(self, x, y, w=None, greedy=False, fix=True, **kw_args):
-        """Layer-wise maximum likelihood (regression.py:391-459).  ``iters`` and other
-        keyword arguments go to the L-BFGS-B driver.  Gradients are finite differences
-        of the device log-marginal for the joint objective (``fix=False``) and inducing-point
-        layers, analytic (``gpar_potri`` + ``gpar_gram_grad``) for the default layer-wise objective."""
+        """Layer-wise maximum likelihood (regression.py:391-459).  ``iters`` and other keyword arguments go to
+        the L-BFGS-B driver.  Gradients are analytic (device kernels) whenever the inputs of the
+        layers being optimised do not depend on the hyper-parameters being optimised: the default layer-wise
+        objective (``fix=True``; dense layers: ``gpar_potri`` + ``gpar_gram_grad``, inducing-point layers: the
+        VFE weights through ``gpar_gram_wgrad``), and the joint objective (``fix=False``) when neither
+        ``replace`` nor imputation feeds posterior means into later layers.  Otherwise (joint objective with
+        ``replace`` / imputed rows / inducing points, where the reference backpropagates through the
+        posterior means) finite differences of the device log-marginal are used."""
         self.condition(x, y, w)
         if greedy:
             raise NotImplementedError("Greedy search is not implemented yet.")
@@ -142,12 +146,12 @@ class GPARRegressor:
                 ctor()
             names = self.vs.match([f"{pi}/*"] if fix else [f"{i}/*" for i in range(pi + 1)])
 
-            # Analytic gradients for the default layer-wise objective on dense layers:
-            # d LML / d theta = sum_ij W_ij dA_ij / d theta with W = 1/2 (alpha alpha^T - A^-1), evaluated
-            # on the device (gpar_potri + gpar_gram_grad) and pushed through the bound transform here.
-            # The joint objective (fix=False: inputs depend on earlier layers' hyper-parameters) and
-            # inducing-point layers keep finite differences.
-            analytic = fix and self.x_ind is None and want_analytic
+            # Analytic gradients: d LML / d theta = sum_ij W_ij dA_ij / d theta with
+            # W = 1/2 (alpha alpha^T - A^-1) (dense) or the VFE weights (inducing points), evaluated on the
+            # device and pushed through the bound transform here.  Valid when the layers' inputs are fixed.
+            inputs_are_data = (self.x_ind is None and not self.replace
+                               and not (self.impute and np.isnan(self.y).any()))
+            analytic = want_analytic and (fix or inputs_are_data)
 
             def objective(z):
                 # every evaluation builds fresh factors: hand the peer-mapped buffers of the previous
@@ -155,13 +159,13 @@ class GPARRegressor:
                 self._release_sharded()
                 self.vs.set_latent_vector(names, z)
                 gpar = _construct_gpar(self, self.vs, self.m, pi + 1)
-                g = {} if analytic else None
+                g = ({} if fix else {"every_layer": True}) if analytic else None
                 try:
                     if fix:
                         val = -gpar.logpdf(fixed_x, y_cached, None, only_last_layer=True, outputs=[pi],
                                            x_ind=fixed_x_ind, grad_out=g)
                     else:
-                        val = -gpar.logpdf(self.x, y_cached, None, only_last_layer=False)
+                        val = -gpar.logpdf(self.x, y_cached, None, only_last_layer=False, grad_out=g)
                 except GparError as e:
                     # a non-positive pivot is a legitimate "infeasible point" for the line search; anything
                     # else (ABI misuse, resource limits, unsupported configuration) must surface
@@ -172,9 +176,12 @@ class GPARRegressor:
                     return (1e300, np.zeros_like(z)) if analytic else 1e300
                 if not analytic:
                     return val
-                if "raw" not in g:  # no observation in this layer: constant objective
-                    return val, np.zeros_like(z)
-                grads = named_gradients(g["layer"].terms, g["raw"].cpu().numpy(), noise_name=f"{pi}/noise")
+                per_layer = g.get("per_layer", {pi: (g["raw"], g["layer"])} if "raw" in g else {})
+                grads = {}  # layers without observations contribute nothing
+                for li, (raw, layer) in per_layer.items():
+                    raw = raw.cpu().numpy() if hasattr(raw, "cpu") else np.asarray(raw)
+                    for name, val_ in named_gradients(layer.terms, raw, noise_name=f"{li}/noise").items():
+                        grads[name] = grads.get(name, 0.0) + val_  # tied scales add up over the layers
                 gz = -self.vs.latent_gradient(names, grads)
                 return val, np.where(np.isfinite(gz), gz, 0.0)
 

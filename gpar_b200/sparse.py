@@ -104,8 +104,9 @@ class SparseFactor:
         # v = L_A^-1 c rides along as an appended row
         self.ws_A, self.info_A = eng.potrf(self.JA, ldz, M, B=self.c, ldb=ldz, nb=1)
         eng.logdet_quad(self.JA, ldz, M, self.c, self.terms, out_off=1)
-        t = eng.backsolve(self.JA, ldz, M, self.ws_A, self.c)
+        t = self.t = eng.backsolve(self.JA, ldz, M, self.ws_A, self.c)  # A^-1 c
         self.beta = eng.backsolve(self.Jz, ldz, M, self.ws_z, t)
+        self.y_host, self.sig_host = np.asarray(y_host, dtype=np.float64), np.asarray(sig_host, dtype=np.float64)
         if prior is not None:
             # posterior-of-posterior mean: m~(q) + k~(q, z) beta = K(q, z_t) (beta_t - h1 + h2) + K(q, z) beta with
             # h1 = L_zt^-T (P_z^T beta), h2 = L_zt^-T L_At^-T (Q_z^T beta)
@@ -121,6 +122,73 @@ class SparseFactor:
             eng.axpy(Mt, 1.0, prior.weights_t(), self.wt)
             eng.axpy(Mt, -1.0, h1, self.wt)
             eng.axpy(Mt, 1.0, h2, self.wt)
+
+    def elbo_grad_raw(self, w_host):
+        """Gradient of this layer's bound w.r.t. its kernel spec and noise (VFE analogue of
+        gpar_potri + gpar_gram_grad; the reference differentiates PseudoObs with autograd,
+        regression.py:434-459).  With R = B^T = K_xz L_z^-T, U_A = L_A^-T, U_z = L_z^-T:
+
+            beta = Sigma^-1 (y - R A^-1 c),  T^T = R L_z^-1,  G2 = Sigma^-1 R (I - A^-1) L_z^-1      (n x M)
+            d ELBO = sum_jm (beta_j (T beta)_m + G2_jm) dk(x_j, z_m) - 1/2 sum_mm' ((T beta)(T beta)^T + G2^T T^T)_mm' dk(z_m, z_m')
+                     - 1/2 sum_j dk(x_j, x_j) / sigma_j + sum_j g_sigma_j dsigma_j
+
+        (weights pinned against finite differences in oracle/vfe_grad.py).  The two weighted Gram-derivative
+        sums run on the device (gpar_gram_wgrad), the O(n) diagonal terms on the host.  Returns the raw
+        chain-rule vector (numpy, layout of gpar_gram_grad; last entry = d ELBO / d noise)."""
+        if self.prior is not None:
+            raise NotImplementedError("gradients of a bound under a sparse posterior are not implemented")
+        from . import _lib
+
+        eng, M, n, ldz, spec = self.eng, self.M, self.n, self.ldz, self.spec
+        raw = np.zeros(_lib.GRAD_NP)
+        if n == 0:
+            return raw
+        sig, y, R = self.sig_host, self.y_host, self.Bt
+        _, Uz = eng.potri(self.Jz, ldz, M, self.ws_z, return_U=True)
+        _, UA = eng.potri(self.JA, ldz, M, self.ws_A, return_U=True)
+        UAt = eng.empty(M * ldz)
+        eng.transpose_scale(UA, ldz, M, M, None, UAt, ldz)  # L_A^-1
+        RU = eng.zeros(n * ldz)
+        eng.gemm_nt(RU, ldz, n, M, R, ldz, UAt, ldz, M, add=True)  # R U_A: rows (L_A^-1 b_j)^T
+        S1 = eng.empty(n * ldz)
+        eng.gather_rows(R, ldz, None, n, M, S1, ldz)
+        eng.gemm_nt(S1, ldz, n, M, RU, ldz, UA, ldz, M, add=False)  # R (I - A^-1)
+        G2 = eng.zeros(n * ldz)
+        eng.gemm_nt(G2, ldz, n, M, S1, ldz, Uz, ldz, M, add=True)  # ... L_z^-1 (row scale 1 / sigma applied below)
+        Tt = eng.zeros(n * ldz)
+        eng.gemm_nt(Tt, ldz, n, M, R, ldz, Uz, ldz, M, add=True)  # T^T = R L_z^-1
+        Rt = eng.empty(n)
+        eng.gemv(R, ldz, n, M, self.t, Rt)
+        beta = (y - Rt.cpu().numpy()) / sig
+        beta_d, inv_sig = eng.to_device(beta), eng.to_device(1.0 / sig)
+        ldn = _even(max(n, 2))
+        RT = eng.empty(M * ldn)
+        eng.transpose_scale(R, ldz, n, M, None, RT, ldn)
+        Bbeta = eng.zeros(ldz)
+        eng.gemv(RT, ldn, M, n, beta_d, Bbeta)
+        Tbeta = eng.backsolve(self.Jz, ldz, M, self.ws_z, Bbeta)
+        raw_zx = eng.gram_wgrad(spec, self.X.t, self.X.ld, n, self.Z.t, self.Z.ld, M, G=G2, ldg=ldz, sx=inv_sig,
+                                ux=beta_d, uy=Tbeta)
+        G2T, TT = eng.empty(M * ldn), RT  # RT is free again
+        eng.transpose_scale(G2, ldz, n, M, inv_sig, G2T, ldn)
+        eng.transpose_scale(Tt, ldz, n, M, None, TT, ldn)
+        Gzz = eng.zeros(M * ldz)
+        eng.gemm_nt(Gzz, ldz, M, M, G2T, ldn, TT, ldn, n, add=True)  # G2^T T^T
+        mhalf = eng.to_device(np.full(M, -0.5))
+        uxz = eng.zeros(ldz)
+        eng.axpy(M, -0.5, Tbeta, uxz)
+        raw_zz = eng.gram_wgrad(spec, self.Z.t, self.Z.ld, M, self.Z.t, self.Z.ld, M, G=Gzz, ldg=ldz, sx=mhalf,
+                                ux=uxz, uy=Tbeta)
+        b2 = eng.row_sqnorm(R, ldz, n, M).cpu().numpy()
+        v2 = eng.row_sqnorm(RU, ldz, n, M).cpu().numpy()
+        raw += raw_zx.cpu().numpy() + raw_zz.cpu().numpy()
+        # O(n) diagonal terms: -1/2 sum_j dk(x_j, x_j) / sigma_j and the noise derivative
+        kdiag, raw_diag = _diag_raw(spec, self.X.to_host(), -0.5 / sig)
+        raw += raw_diag
+        P = 1.0 / sig - v2 / sig ** 2
+        g_sigma = 0.5 * (beta ** 2 - P) + 0.5 * (kdiag - b2) / sig ** 2
+        raw[_lib.GRAD_NP - 1] = float(np.sum(g_sigma / np.asarray(w_host, dtype=np.float64)))
+        return raw
 
     def weights_t(self):
         """Weights of K(., z) in this factor's own posterior mean (a prior-level factor: beta)."""
@@ -179,6 +247,31 @@ class SparseFactor:
                 eng.sample_affine(Cs, ldc, ns, Zc, y_col[S * r0:], S, batch=B, strideC=ns * ldc, mean=mean[r0:],
                                   sd=sd, Z2=Z2c, strideSd=0)
         return f_col, y_col, mean
+
+
+def _diag_raw(spec, Xh, g):
+    """k(x_j, x_j) per row and the raw chain-rule sums of sum_j g_j dk(x_j, x_j) / d spec (layout of
+    gpar_gram_grad): EQ / RQ / const terms contribute their variance only (zero distance); a linear term
+    v sum_f phi_f(x)^2 also feeds the S1 slot of its features (d / d a_f = 2 S1_f / a_f)."""
+    from . import _lib
+
+    raw = np.zeros(_lib.GRAD_NP)
+    kdiag = np.zeros(Xh.shape[0])
+    base = 2 * _lib.MAX_TERMS
+    for t in range(spec.n_terms):
+        T = spec.terms[t]
+        if T.type == _lib.TERM_LINEAR:
+            acc = np.zeros(Xh.shape[0])
+            for f in range(T.f_begin, T.f_end):
+                phi2 = (Xh[:, spec.feat_col[f]] * spec.feat_a[f]) ** 2
+                raw[base + 2 * f] += T.variance * float(np.sum(g * phi2))
+                acc += phi2
+            raw[2 * t] += float(np.sum(g * acc))
+            kdiag += T.variance * acc
+        else:
+            raw[2 * t] += float(np.sum(g))
+            kdiag += T.variance
+    return kdiag, raw
 
 
 def _layer(model):
@@ -244,7 +337,7 @@ def _zd(gpar, x_ind, p):
 
 
 def logpdf_sparse(gpar, x, y, w, only_last_layer, return_inputs, x_ind, outputs, sample_missing=False,
-                  normals=None):
+                  normals=None, grad_out=None):
     eng = gpar.engine
     if not isinstance(y, dict):
         y = np.asarray(y, dtype=np.float64)
@@ -272,6 +365,10 @@ def logpdf_sparse(gpar, x, y, w, only_last_layer, return_inputs, x_ind, outputs,
                                      sample_missing=sample_missing, normals=normals)
         if (not only_last_layer) or is_last:
             slots.append((fac.elbo_slot(), fac.n))
+            if grad_out is not None and is_last and fac.n > 0:
+                avail = ~np.isnan(y_i[:, 0])
+                grad_out["raw"] = fac.elbo_grad_raw(w_i[avail])
+                grad_out["layer"] = layer
     eng.check_infos()
     if return_inputs:
         return xd, zd

@@ -164,6 +164,15 @@ int gpar_gemm_nt(double* C, int64_t ldc, int64_t m, int64_t n, const double* A, 
 size_t gpar_potri_scratch_bytes(int64_t n);
 int gpar_potri(const double* L, int64_t ldl, int64_t n, const double* ws, double* U, int64_t ldu, double* Ainv,
                int64_t lda, double* scratch, void* stream);
+/* gpar_gram_wgrad: the same raw sums for a rectangular block k(x_i, y_j) (i < nx, j < ny) under explicit weights
+ * W_ij = ux_i uy_j + sx_i G_ij (G nx x ny row major with leading dimension ldg; G, sx, ux/uy optional; every pair
+ * counted once; out[208] is not touched by it = 0) -- the sum G_zx dK_zx and sum G_zz dK_zz terms of the
+ * gradient of the VFE bound (inducing-point layers of `fit`).  gpar_row_sqnorm: out[i] = sum_c A[i][c]^2. */
+size_t gpar_gram_wgrad_workspace_bytes(int64_t nx, int64_t ny);
+int gpar_gram_wgrad(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t nx, const double* Y,
+                    int64_t ldy, int64_t ny, const double* G, int64_t ldg, const double* sx, const double* ux,
+                    const double* uy, double* workspace, double* out, void* stream);
+int gpar_row_sqnorm(const double* A, int64_t lda, int64_t n, int64_t k, double* out, void* stream);
 size_t gpar_gram_grad_workspace_bytes(int64_t n);
 int gpar_gram_grad(const gpar_kernel_spec_t* spec, const double* X, int64_t ldx, int64_t n, const double* alpha,
                    const double* Ainv, int64_t lda, const double* dvec, double* workspace, double* out,

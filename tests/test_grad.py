@@ -248,3 +248,91 @@ def test_fit_analytic_gradient_matches_fd_and_improves(eng):
     reg.fit(data["x"], data["y"], iters=15)
     lp1 = reg.logpdf(data["x"], data["y"])
     assert lp1 > lp0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,n", [(24, 150), (160, 700)])
+def test_vfe_gradient_matches_finite_differences(eng, M, n):
+    """Inducing-point layers of ``fit`` (regression.py:434-459 through PseudoObs): the device gradient of the VFE
+    bound (SparseFactor.elbo_grad_raw: gpar_gram_wgrad over K_xz and K_zz + host diagonal terms; weights of
+    oracle/vfe_grad.py) against central differences of the device bound, layer 1 of a two-layer model
+    (EQ + input-linear + output-linear + output-EQ kernel, per-row weights).  M = 160 spans two Cholesky tiles."""
+    import bench
+    from gpar_b200 import GPARRegressor
+    from gpar_b200.model import per_output
+    from gpar_b200.regression import _construct_gpar
+    from gpar_b200.spec import named_gradients as ng
+
+    data = bench.make_data(n=n, m=2, p=2, ns=10, S=1, missing=0.1)
+    z = np.random.default_rng(4).uniform(0, 1, (M, 2))
+    kw = dict(scale=0.5, noise=0.2, linear=True, linear_scale=5.0, nonlinear=True, nonlinear_scale=1.0, input_linear=True,
+              replace=True, impute=True, normalise_y=True, x_ind=z)
+    reg = GPARRegressor(engine=eng, **kw)
+    w = np.random.default_rng(9).uniform(0.5, 2.0, data["y"].shape)
+    reg.condition(data["x"], data["y"], w)
+    y_cached = {k: list(per_output(reg.y, reg.w, keep=k)) for k in [True, False]}
+    pi = 1
+    gp = _construct_gpar(reg, reg.vs, reg.m, pi + 1)
+    fx, fxi = gp.logpdf(reg.x, y_cached, None, only_last_layer=True, outputs=list(range(pi)), return_inputs=True)
+    for ctor in _construct_gpar(reg, reg.vs, reg.m, pi + 1).layers:
+        ctor()
+    names = reg.vs.match([f"{pi}/*"])
+    z0 = reg.vs.get_latent_vector(names)
+
+    def val_grad(zv, want_grad):
+        reg.vs.set_latent_vector(names, zv)
+        g = {} if want_grad else None
+        v = _construct_gpar(reg, reg.vs, reg.m, pi + 1).logpdf(fx, y_cached, None, only_last_layer=True, outputs=[pi],
+                                                             x_ind=fxi, grad_out=g)
+        if not want_grad:
+            return v
+        return v, reg.vs.latent_gradient(names, ng(g["layer"].terms, np.asarray(g["raw"]), noise_name=f"{pi}/noise"))
+
+    v, gz = val_grad(z0, True)
+    fd = np.zeros_like(z0)
+    for k in range(z0.size):
+        zp, zm = z0.copy(), z0.copy()
+        zp[k] += 1e-5; zm[k] -= 1e-5
+        fd[k] = (val_grad(zp, False) - val_grad(zm, False)) / 2e-5
+    reg.vs.set_latent_vector(names, z0)
+    np.testing.assert_allclose(gz, fd, rtol=2e-4, atol=2e-5 * max(1.0, np.abs(fd).max()))
+
+
+@pytest.mark.gpu
+def test_fit_with_inducing_points_and_joint_objective_use_analytic_gradients(eng, monkeypatch):
+    """fit(x_ind=...) and fit(fix=False) on data-only inputs run L-BFGS with jac=True (no finite differences):
+    the number of bound evaluations stays at the optimiser's own count, and the objective improves."""
+    import bench
+    import gpar_b200.regression as R
+    from gpar_b200 import GPARRegressor
+
+    calls = []
+    real_minimize = R.minimize
+
+    def spy(fun, x0, jac=None, **kw):
+        calls.append(bool(jac))
+        return real_minimize(fun, x0, jac=jac, **kw)
+
+    monkeypatch.setattr(R, "minimize", spy)
+    data = bench.make_data(n=300, m=2, p=2, ns=10, S=1, missing=0.1)
+    z = np.random.default_rng(4).uniform(0, 1, (40, 2))
+    kw = dict(scale=0.5, noise=0.2, linear=True, linear_scale=5.0, nonlinear=True, nonlinear_scale=1.0, replace=True,
+              impute=True, normalise_y=True)
+    reg = GPARRegressor(engine=eng, x_ind=z, **kw)
+    reg.condition(data["x"], data["y"])
+    lp0 = reg.logpdf(data["x"], data["y"])
+    reg.fit(data["x"], data["y"], iters=10)
+    assert calls == [True, True] and reg.logpdf(data["x"], data["y"]) > lp0
+    # joint objective, no replace / no missing data: inputs are data => analytic for all layers at once
+    calls.clear()
+    full = bench.make_data(n=200, m=2, p=3, ns=10, S=1, missing=0.0)
+    reg2 = GPARRegressor(engine=eng, **{**kw, "replace": False, "impute": True, "scale_tie": True})
+    reg2.condition(full["x"], full["y"])
+    lp0 = reg2.logpdf(full["x"], full["y"])
+    reg2.fit(full["x"], full["y"], fix=False, iters=8)
+    assert calls == [True, True, True] and reg2.logpdf(full["x"], full["y"]) > lp0
+    # joint objective with replace: posterior means feed later layers => finite differences (stated in fit)
+    calls.clear()
+    reg3 = GPARRegressor(engine=eng, **kw)
+    reg3.fit(data["x"], data["y"], fix=False, iters=2)
+    assert calls == [False, False]
