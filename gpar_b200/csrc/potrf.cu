@@ -1033,7 +1033,14 @@ __host__ __device__ __forceinline__ void df_decode(int t, const DfShape& sh, int
     if (idx == 0) { kind = TASK_HEAD; i = g + 2; j = g + 1; }
     else if (idx == 1) { kind = TASK_PLAIN; i = g + 2; }
     else if (idx == 2) { kind = TASK_PRE; i = g + 2; j = g + 2; }
-    else { kind = TASK_PLAIN; i = g + idx; }
+    else {
+      // the remaining tiles of the column: rows g + 3 .. rows_total - 1, ascending in even columns and descending
+      // in odd ones (boustrophedon): the row panels L_i,0..j streamed last by column g are the first ones column
+      // g + 1 asks for, so that an L2-sized part of them is still resident (a fixed direction re-streams the
+      // whole panel set from HBM once it exceeds the 126 MB L2: columns 24..42 at nt = 66)
+      kind = TASK_PLAIN;
+      i = (g & 1) ? (rows_total - 1) - (idx - 3) : g + idx;
+    }
   } else {
     kind = TASK_PLAIN;
     i = ((g + 1 < nt) ? g + 2 : g + 1) + idx;
