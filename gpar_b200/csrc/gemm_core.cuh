@@ -83,6 +83,10 @@ __device__ __forceinline__ unsigned block_mask(int wm, int wn, int valid_rows) {
     for (int h = 0; h < 2; ++h) {
       bool on = acc_row(wm, i) < valid_rows;
       if (MODE == 1) on = on && (wn * 64 + 32 * h <= acc_row(wm, i) + 7);
+      // MODE 3 (diagonal-tile SYRK at 64 x 64 granularity): the quadrant rows 0..63 x columns 64..127 lies above
+      // the diagonal -- the right n-warps skip their first two row groups and run a straight-line half body
+      // (unlike the 8 x 32 masks of MODE 1, whose per-block branches break the DMMA / LDS software pipeline)
+      if (MODE == 3) on = on && !(wn == 1 && i < 2);
       if (on) m |= 1u << (2 * i + h);
     }
   return m;
@@ -160,6 +164,11 @@ __device__ __forceinline__ void mma_chunk(const GemmStage& st, Acc& acc, int wm,
     if (mask == 0xFFu) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    } else if (mask == 0xF0u) {  // row groups 2, 3 only (MODE 3, right n-warps)
+#pragma unroll
+      for (int i = 2; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     } else if (mask == 0x03u) {  // first row group only (32-row operands: the L^-T sweep of gpar_potri)

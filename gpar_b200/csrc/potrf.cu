@@ -1143,6 +1143,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
         acc_zero(acc);
         // (the masked lower-triangular MODE 1 path is slower than the full tile: its branches break
         //  the DMMA/LDS software pipeline; measured 2x per chunk)
+#ifndef GPAR_PRE_FULL
+        if (pre && valid == TILE)  // diagonal tile: only col <= row is stored -- skip the upper-right 64 x 64 quadrant
+          gemm_nt_mainloop_dep<3>(stages, rowi + (int64_t)k0 * TILE, ldi, valid, rowj + (int64_t)k0 * TILE, p.lda, kb,
+                                  (k1 - k0) * TILE, acc, ready_i + k0, ready_j + k0, multi, T, ldi);
+        else
+#endif
         gemm_nt_mainloop_dep<0>(stages, rowi + (int64_t)k0 * TILE, ldi, valid, rowj + (int64_t)k0 * TILE, p.lda, kb,
                                 (k1 - k0) * TILE, acc, ready_i + k0, ready_j + k0, multi, T, ldi);
         DFP_MARK(1);

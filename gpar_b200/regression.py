@@ -102,6 +102,7 @@ class GPARRegressor:
         self.w = _init_weights(w, self.y)
         self.n, self.m = self.x.shape
         self.p = self.y.shape[1]
+        self._check_limits(self.m, self.p)
         if self.normalise_y:
             means, stds = [], []
             for i in range(self.p):
@@ -117,6 +118,25 @@ class GPARRegressor:
         else:
             self._unnormalise_y, self._normalise_y, self._norm = _identity, _identity, None
         self.is_conditioned = True
+
+    def _check_limits(self, m, p):
+        """The device kernel spec is a fixed-size POD (include/gpar_b200.h: GPAR_MAX_FEATS = 96 features,
+        GPAR_MAX_TERMS = 8 terms) and the Gram kernels stage 64-row input tiles in shared memory (about 200
+        input columns).  The reference has no such limits: fail here, with the numbers, rather than deep inside a
+        layer constructor."""
+        from ._lib import MAX_FEATS
+
+        cfg = self.model_config
+        markov = cfg["markov"]
+        p_num = (p - 1) if markov is None else min(p - 1, markov)
+        feats = m + (3 * m if cfg["per"] else 0) + (m if cfg["input_linear"] else 0)
+        feats += (p_num if cfg["linear"] else 0) + (p_num if cfg["nonlinear"] else 0)
+        if feats > MAX_FEATS:
+            raise ValueError(f"the last layer's kernel needs {feats} input features (m={m}, previous outputs used="
+                             f"{p_num}); the device kernel spec holds {MAX_FEATS}: set markov=k to cap the number of "
+                             "previous outputs per layer")
+        if m + p > 200:
+            raise ValueError(f"{m + p} input columns (m + p) exceed what the Gram kernels stage in shared memory (~200)")
 
     def fit(self, x, y, w=None, greedy=False, fix=True, **kw_args):
         """Layer-wise maximum likelihood (regression.py:391-459).  ``iters`` and other keyword arguments go to

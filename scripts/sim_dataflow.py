@@ -69,7 +69,10 @@ def simulate(n, nb=1, grid=148, P=None, verbose=False):
             return
         if ("r", j, j) not in flags:
             yield ("wait", ("r", j, j))
-        yield ("delay", P["solve"] if i < nt else P["solve"] * 0.5)
+        if kind == HEAD and "head_solve" in P:
+            yield ("delay", P["head_solve"])
+        else:
+            yield ("delay", P["solve"] if i < nt else P["solve"] * 0.5)
         yield ("set", ("r", i, j))
         if kind == HEAD:
             k = i

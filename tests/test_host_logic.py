@@ -252,3 +252,15 @@ def test_numpy_virtual_index_reproduces_np_percentile():
             d = hi - lo
             got = hi - d * (1.0 - g) if g >= 0.5 else lo + d * g
             assert got == np.percentile(a, q), (ns, q)
+
+
+def test_regressor_reports_kernel_spec_limits_at_condition():
+    """Wide fully-connected models exceed the fixed-size device kernel spec (GPAR_MAX_FEATS): the regressor says
+    so when the data arrives, and markov=k lifts it."""
+    from gpar_b200 import GPARRegressor
+
+    x = np.zeros((4, 2)); y = np.zeros((4, 60))
+    reg = GPARRegressor(linear=True, nonlinear=True)
+    with pytest.raises(ValueError, match="markov"):
+        reg.condition(x, y)
+    GPARRegressor(linear=True, nonlinear=True, markov=3).condition(x, y)
