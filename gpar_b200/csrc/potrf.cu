@@ -31,8 +31,8 @@ constexpr int DLD = 132;  // row stride of the tile in shared memory: = 4 (mod 1
                           // fragment loads bank-conflict free; rows stay 16-byte aligned for cp.async
 constexpr int PANEL = 32; // panel width of the in-tile blocked factorisation
 constexpr double REFINE_KAPPA = 1.0e3;  // kappa_inf(L_kk) above which the tile solves are refined
-// shared layout: Ls[TILE][DLD] | rdiag[TILE] | LT[PANEL][PANEL] | red[32] | rowL[TILE] | ints
-constexpr size_t DIAG_SMEM_BYTES = sizeof(double) * (TILE * DLD + TILE + PANEL * PANEL + 32 + TILE) + 16;
+// shared layout: Ls[TILE][DLD] | rdiag[TILE] | LT[PANEL][PANEL] | red[32] | rowL[TILE] | isumP[8][TILE] | ints
+constexpr size_t DIAG_SMEM_BYTES = sizeof(double) * (TILE * DLD + TILE + PANEL * PANEL + 32 + TILE + 8 * TILE) + 16;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
@@ -369,23 +369,78 @@ __device__ __forceinline__ void rank32_update(double* __restrict__ Ls, const dou
 // inverse costs no extra phase.  Four panel steps of width 32: warp 0 factors the diagonal block
 // (shuffle pivots, registers), warps 1-4 solve the 128 rows against it as its columns appear, then
 // all warps apply the rank-32 DMMA update to the columns beyond the panel.
+//
+// panel_flags (single GPU, optional): four flags of this tile.  Row panel p of the results -- rows [32 p, 32 p + 32)
+// of L_kk and of L_kk^-1 -- is final as soon as panel step p is over; it is written out right then (by the warps
+// that idle during the next panel step) and panel_flags[p] is released, so that the HEAD task of the next
+// column can run its 32-column blocks behind the factorisation instead of after it (head_pipelined).
 template <bool MULTI>
 __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* __restrict__ Atile, int64_t lda,
                                                  int kb, int64_t j0, double* __restrict__ ws,
                                                  double* __restrict__ flag_out, int32_t* __restrict__ info_b,
-                                                 int* ready_flag, const Peers* pe, long long* prof) {
+                                                 int* ready_flag, const Peers* pe, long long* prof,
+                                                 int* panel_flags = nullptr) {
 #define GPAR_PROF(i) do { if (prof && threadIdx.x == 0) prof[i] = clock64(); } while (0)
   double* Ls = reinterpret_cast<double*>(smem_raw);
   double* rdiag = Ls + TILE * DLD;
   double* LT = rdiag + TILE;
   double* red = LT + PANEL * PANEL;  // 32 doubles of reduction scratch
   double* rowL = red + 32;           // running row sums of |L| (accumulated panel by panel)
-  int* s_int = reinterpret_cast<int*>(rowL + TILE);  // [0] first bad pivot, [1] refine
+  double* isumP = rowL + TILE;       // [8][TILE]: per-warp partial row sums of |Linv| (panel-wise write-out)
+  int* s_int = reinterpret_cast<int*>(isumP + 8 * TILE);  // [0] first bad pivot, [1] refine
   const int tid = threadIdx.x, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
   const int warp = canonical_warp();
   const bool multi = MULTI && (pe != nullptr) && (pe->world > 1);  // MULTI = false: all peer code compiles out
   if (tid == 0) s_int[0] = 0;
   if (tid < TILE) rowL[tid] = 0.0;
+  const bool panelwise = !multi && (panel_flags != nullptr);
+  if (panelwise)
+    for (int q = tid; q < 8 * TILE; q += 256) isumP[q] = 0.0;
+  const bool vec_l = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(Atile) & 15) == 0);
+  // Write row panel pp of Linv (to ws) and of L (to Atile) with the warps wfirst .. wfirst + nw - 1.
+  // Linv[r][c] = Ls[c][r] (c < r), rdiag[r] at c = r, zeros up to the end of the diagonal 32-block; lanes run
+  // along r (conflict-free), a lane assembles 4 consecutive c.  L rows: lanes along the columns.
+  auto write_panel = [&](int pp, int wfirst, int nw) {
+    if (warp < wfirst || warp >= wfirst + nw) return;
+    const int wl = warp - wfirst;
+    const int r = PANEL * pp + lane;
+    double isum = 0.0;
+    for (int cg = wl; cg < 8 * (pp + 1); cg += nw) {
+      const int c = 4 * cg;
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double off = Ls[(c + q) * DLD + r];
+        v[q] = (c + q < r) ? off : ((c + q == r) ? rdiag[r] : 0.0);
+      }
+      if (r < kb) {
+        double* dst = ws + r * TILE + c;
+        *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
+        isum += (fabs(v[0]) + fabs(v[1])) + (fabs(v[2]) + fabs(v[3]));
+      }
+    }
+    isumP[warp * TILE + r] += isum;  // slot (warp, r) belongs to this lane alone
+    const int c = 4 * lane;
+    for (int rr = PANEL * pp + wl; rr < PANEL * pp + PANEL && rr < kb; rr += nw) {
+      if (c > (rr | 31) || c >= kb) continue;
+      const double2 v0 = *reinterpret_cast<const double2*>(Ls + rr * DLD + c);
+      const double2 v1 = *reinterpret_cast<const double2*>(Ls + rr * DLD + c + 2);
+      double v[4] = {v0.x, v0.y, v1.x, v1.y};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (c + q > rr) v[q] = 0.0;
+      double* pd = Atile + (int64_t)rr * lda + c;
+      if (vec_l && c + 3 < kb) {
+        *reinterpret_cast<double2*>(pd) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(pd + 2) = make_double2(v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (c + q < kb) pd[q] = v[q];
+      }
+    }
+  };
   GPAR_PROF(1);
 #pragma unroll 1
   for (int p = 0; p < TILE / PANEL; ++p) {
@@ -399,8 +454,16 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
       panel_solve_warp(Ls, rdiag, LT, rowL, c0, (warp - 1) * 32 + lane);
       if (prof && lane == 0 && (warp == 1 || warp == 4)) prof[(warp == 1 ? 20 : 24) + p] = clock64();
     } else if (p >= 1) {
-      // warps 5-7 idle through the panel step: they finish the update of panel p - 1 on the columns
-      // beyond this panel (disjoint from everything the panel step touches)
+      // warps 5-7 idle through the panel step.  Row panel p - 1 of L and Linv is final: out it goes, flag up
+      // (everything it reads -- columns < 32 p of all rows, rdiag -- is left alone by this panel step).
+      if (panelwise) {
+        write_panel(p - 1, 5, 3);
+        __threadfence();
+        named_bar_sync(6, 96);
+        if (warp == 5 && lane == 0) st_release(panel_flags + (p - 1), 1);
+      }
+      // then they finish the update of panel p - 1 on the columns beyond this panel (disjoint from
+      // everything the panel step touches)
       rank32_update(Ls, rdiag, p - 1, p + 1, TILE / PANEL - 1, 5, 3, warp, gid, tig);
     }
     __syncthreads();
@@ -457,13 +520,14 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
       for (int rb = 0; rb < 4; ++rb) LT[warp * TILE + 32 * rb + lane] = isum[rb];
     }
   };
-  write_linv(PEERS_FIRST);
+  if (panelwise) write_panel(TILE / PANEL - 1, 0, 8); else write_linv(PEERS_FIRST);
   GPAR_PROF(14);
   __syncthreads();
   if (tid < TILE) {
     double s = 0.0;
+    const double* part = panelwise ? isumP : LT;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += LT[w * TILE + tid];
+    for (int w = 0; w < 8; ++w) s += (tid < kb) ? part[w * TILE + tid] : 0.0;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, off));
     if (lane == 0) red[8 + warp] = s;
@@ -485,9 +549,19 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
   fence_publish(pe);
   __syncthreads();
   const bool refine = s_int[1] != 0;
-  // Well-conditioned tile: consumers only read Linv (L_kk is read by the refined solves), so the flag
-  // goes up now -- on this rank and, multi-GPU, on the rank that owns the next tile row.
-  const bool early = ready_flag && !refine;
+  if (panelwise) {  // every row panel of L and Linv is out (the last one just now), the refine flag is set
+    if (tid == 0) {
+      st_release(panel_flags + (TILE / PANEL - 1), 1);
+      if (ready_flag) st_release(ready_flag, 1);
+    }
+    GPAR_PROF(11);
+    GPAR_PROF(12);
+    return;
+  }
+  // Well-conditioned tile on a single GPU: consumers that only read Linv could be released before L_kk is
+  // written.  The HEAD task of the next column reads the row panels of L_kk (head_pipelined), so with several
+  // GPUs (no panel flags) the flag goes up once both are out.
+  const bool early = ready_flag && !refine && !multi;
   if (early && tid == 0) publish_flag(ready_flag, pe, PEERS_FIRST);
   if (multi && pe->world > 2) write_linv(PEERS_REST);
   GPAR_PROF(11);
@@ -777,6 +851,10 @@ __device__ __forceinline__ void wait_ready(const int* flag, bool sys = false) {
   }
 }
 
+__device__ __forceinline__ void wait_count(const int* counter, int target) {
+  while (ld_acquire(counter) < target) __nanosleep(40);
+}
+
 // gemm_nt_mainloop over K = 128 * ktiles with per-k-tile dependency waits on readyA[kt], readyB[kt]:
 // every thread acquires the flags before it issues its copies of the first chunk of a k-tile.
 // (Measured alternatives: polling the flags in the background so that landed chunks are never
@@ -833,17 +911,16 @@ __device__ __forceinline__ void acc_to_smem(double* __restrict__ Xs, const Acc& 
           make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
-// acc = lower part of Xs Xs^T (K = 128), both operands straight from the shared tile.  Only the
-// 8 x 32 blocks that touch the lower triangle are computed (static per-warp block lists).
-__device__ __forceinline__ void syrk_from_smem(const double* __restrict__ Xs, Acc& acc) {
+// acc += lower part of Xs[:, k_lo:k_hi] Xs[:, k_lo:k_hi]^T, both operands straight from the shared tile.  Only
+// the 8 x 32 blocks that touch the lower triangle are computed (static per-warp block lists).
+__device__ __forceinline__ void syrk_from_smem_range(const double* __restrict__ Xs, Acc& acc, int k_lo, int k_hi) {
   const int warp = canonical_warp(), lane = threadIdx.x & 31;
   const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
   const double* pa = Xs + (wm * 8 + gid) * DLD + tig;
   const double* pb = Xs + (wn * 64 + gid) * DLD + tig;
-  acc_zero(acc);
   if (wn == 0) {  // columns 0..63: every row group, except (i = 0, columns 32..63)
 #pragma unroll 2
-    for (int kk = 0; kk < TILE; kk += 4) {
+    for (int kk = k_lo; kk < k_hi; kk += 4) {
       double a[4], b[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = pa[i * 32 * DLD + kk];
@@ -860,7 +937,7 @@ __device__ __forceinline__ void syrk_from_smem(const double* __restrict__ Xs, Ac
     }
   } else {  // columns 64..127: row groups i = 2 (columns 64..95) and i = 3 (all)
 #pragma unroll 2
-    for (int kk = 0; kk < TILE; kk += 4) {
+    for (int kk = k_lo; kk < k_hi; kk += 4) {
       double a[2], b[8];
       a[0] = pa[2 * 32 * DLD + kk];
       a[1] = pa[3 * 32 * DLD + kk];
@@ -871,6 +948,160 @@ __device__ __forceinline__ void syrk_from_smem(const double* __restrict__ Xs, Ac
 #pragma unroll
       for (int j = 0; j < 8; ++j) dmma884(acc[3][j][0], acc[3][j][1], a[1], b[j]);
     }
+  }
+}
+__device__ __forceinline__ void syrk_from_smem(const double* __restrict__ Xs, Acc& acc) {
+  acc_zero(acc);
+  syrk_from_smem_range(Xs, acc, 0, TILE);
+}
+
+// ---- HEAD task, pipelined behind the diagonal factor of the previous column ------------------------
+// X L_jj^T = T by blocked forward substitution over four 32-column blocks, in place in the shared tile Ts:
+//     X_cb = (T_cb - sum_{cb' < cb} X_cb' L_{cb,cb'}^T) Linv_{cb,cb}^T,
+// block cb needing only row panel cb of L_jj and the diagonal 32-block of L_jj^-1 -- exactly what
+// diag_factor_core publishes after its panel step cb (panel_flags).  S += X_cb X_cb^T follows each block, so
+// that when the last panel flag arrives one block solve and a quarter of the SYRK are left instead of
+// solve + SYRK of the whole tile (17 + 11 us on the column chain).
+typedef double AccP[4][2][2];  // 128 x 32 output: row groups acc_row(wm, i), column tiles wn * 16 + 8 j
+
+// accp += As[:, 0:K] Bs[:, 0:K]^T; As: 128 rows, stride DLD; Bs: 32 rows, stride ldb (= 4 mod 16 doubles).
+__device__ __forceinline__ void mma_panel(const double* __restrict__ As, const double* __restrict__ Bs, int ldb, int K,
+                                          AccP& acc, int wm, int wn, int gid, int tig) {
+  const double* pa = As + (wm * 8 + gid) * DLD + tig;
+  const double* pb = Bs + (wn * 16 + gid) * ldb + tig;
+#pragma unroll 4
+  for (int kk = 0; kk < K; kk += 4) {
+    double a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = pa[i * 32 * DLD + kk];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) b[j] = pb[j * 8 * ldb + kk];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+constexpr int LDD = PANEL + 4;  // stride of the 32 x 32 diagonal inverse block in shared memory
+// shared layout of the pipelined HEAD: Ts[TILE][DLD] | Lp[PANEL][DLD] | Ld[PANEL][LDD]
+constexpr size_t HEADP_SMEM_BYTES = sizeof(double) * (TILE * DLD + PANEL * DLD + PANEL * LDD);
+
+// T (global, rows x 128) -> Ts (zeros beyond `rows`).  All threads; ends with a barrier.
+__device__ __forceinline__ void load_tile_to_smem(double* __restrict__ Ts, const double* __restrict__ T, int64_t ldt,
+                                                  int rows) {
+#pragma unroll 8
+  for (int q = 0; q < 32; ++q) {
+    const int idx = threadIdx.x + q * GEMM_THREADS;  // row r, double2 column c
+    const int r = idx >> 6, c = (idx & 63) * 2;
+    cp_async16(&Ts[r * DLD + c], (r < rows) ? (T + (int64_t)r * ldt + c) : T, (r < rows) ? 16 : 0);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+// Ts (shared) -> dst (global tile, rows x 128).  All threads; no barrier.
+__device__ __forceinline__ void store_tile_from_smem(double* __restrict__ dst, int64_t ldd, int rows,
+                                                     const double* __restrict__ Ts) {
+#pragma unroll 8
+  for (int q = 0; q < 32; ++q) {
+    const int idx = threadIdx.x + q * GEMM_THREADS;
+    const int r = idx >> 6, c = (idx & 63) * 2;
+    if (r < rows) *reinterpret_cast<double2*>(dst + (int64_t)r * ldd + c) = *reinterpret_cast<const double2*>(Ts + r * DLD + c);
+  }
+}
+
+// Ts (shared) = T (global tile, rows x 128) - acc (accumulator layout of MODE 0); zeros beyond `rows`.
+// All threads; no barrier.
+__device__ __forceinline__ void tile_sub_to_smem(double* __restrict__ Ts, const double* __restrict__ T, int64_t ldt,
+                                                 int rows, const Acc& acc) {
+  const int warp = canonical_warp(), lane = threadIdx.x & 31;
+  const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int ih = 0; ih < 2; ++ih) {
+    double2 old[2][8];
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii) {
+      const int r = acc_row(wm, 2 * ih + ii) + gid;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        old[ii][j] = (r < rows) ? __ldcg(reinterpret_cast<const double2*>(T + (int64_t)r * ldt + wn * 64 + j * 8 + 2 * tig))
+                                : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii) {
+      const int i = 2 * ih + ii;
+      const int r = acc_row(wm, i) + gid;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<double2*>(Ts + r * DLD + wn * 64 + j * 8 + 2 * tig) =
+            (r < rows) ? make_double2(old[ii][j].x - acc[i][j][0], old[ii][j].y - acc[i][j][1]) : make_double2(0.0, 0.0);
+    }
+  }
+}
+
+// The four blocks.  Ts holds T on entry and X on return; S (zeroed here) holds the lower part of X X^T.
+// Ljj: tile (j, j) of the matrix (global, ld ldl); Linv: its inverse tile (global, ld 128).
+// wait_panel(cb) blocks until row panel cb of both is in global memory.
+template <typename WaitFn>
+__device__ __forceinline__ void head_blocks(unsigned char* smem_raw, const double* __restrict__ Ljj, int64_t ldl,
+                                            const double* __restrict__ Linv, Acc& S, WaitFn wait_panel) {
+  double* Ts = reinterpret_cast<double*>(smem_raw);
+  double* Lp = Ts + TILE * DLD;
+  double* Ld = Lp + PANEL * DLD;
+  const int warp = canonical_warp(), lane = threadIdx.x & 31;
+  const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
+  acc_zero(S);
+#pragma unroll 1
+  for (int cb = 0; cb < TILE / PANEL; ++cb) {
+    const int c0 = PANEL * cb;
+    wait_panel(cb);
+    // row panel cb of L_jj (columns < c0) and the diagonal 32-block of Linv (zeros above its diagonal)
+    for (int idx = threadIdx.x; idx < PANEL * (c0 / 2); idx += GEMM_THREADS) {
+      const int r = idx / (c0 / 2), c = (idx % (c0 / 2)) * 2;
+      cp_async16(&Lp[r * DLD + c], Ljj + (int64_t)(c0 + r) * ldl + c, 16);
+    }
+    for (int idx = threadIdx.x; idx < PANEL * (PANEL / 2); idx += GEMM_THREADS) {
+      const int r = idx / (PANEL / 2), c = (idx % (PANEL / 2)) * 2;
+      cp_async16(&Ld[r * LDD + c], Linv + (int64_t)(c0 + r) * TILE + c0 + c, 16);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    AccP u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) u[i][j][0] = u[i][j][1] = 0.0;
+    if (cb > 0) mma_panel(Ts, Lp, DLD, c0, u, wm, wn, gid, tig);  // sum_{cb' < cb} X_cb' L_{cb,cb'}^T
+    // V = T_cb - U, in place (nobody reads the columns of block cb during the update above)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double2* pv = reinterpret_cast<double2*>(Ts + (acc_row(wm, i) + gid) * DLD + c0 + wn * 16 + 8 * j + 2 * tig);
+        double2 v = *pv;
+        v.x -= u[i][j][0];
+        v.y -= u[i][j][1];
+        *pv = v;
+      }
+    __syncthreads();
+    AccP x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) x[i][j][0] = x[i][j][1] = 0.0;
+    mma_panel(Ts + c0, Ld, LDD, PANEL, x, wm, wn, gid, tig);  // X_cb = V Linv_{cb,cb}^T
+    __syncthreads();  // every warp has read V
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        *reinterpret_cast<double2*>(Ts + (acc_row(wm, i) + gid) * DLD + c0 + wn * 16 + 8 * j + 2 * tig) =
+            make_double2(x[i][j][0], x[i][j][1]);
+    __syncthreads();
+    syrk_from_smem_range(Ts, S, c0, c0 + PANEL);
   }
 }
 
@@ -921,7 +1152,94 @@ __device__ __forceinline__ void assemble_diag(double* __restrict__ Ls, const dou
   }
 }
 
+// The phases of a tile task as out-of-line functions, each with its own accumulators and its own register
+// allocation.  Inlined into one kernel body they compete for the 255 registers of the persistent kernel and the
+// main K-loop pays for every line added elsewhere (18.5 instead of 17.75 us per k-tile with the pipelined HEAD
+// inlined).  No accumulator crosses a call: an Acc passed by reference would pin the caller's accumulators to
+// local memory.
+struct TaskCtx {
+  double* rowi; int64_t ldi; int valid;      // tile row i of the matrix (or of the appended rows)
+  const double* rowj; int64_t lda; int kb;   // tile row j
+  int i, j, k0, k1a, k1, part;               // K-range of this part: [k0, k1a) through the ring (+ [k1a, k1) for a HEAD)
+  bool pre, head, multi;
+  const int* ready_i; const int* ready_j;    // ready flags of the two tile rows
+  int* ready_ij;                             // flag of tile (i, j)
+  int* pcount;                               // K-parts already subtracted from tile (i, j)
+  const int* pfl;                            // panel flags of tile (j, j) (single GPU)
+  const double* Linv; const double* refine_flag;
+  const int* pre_count; int pre_parts;       // HEAD: K-part counter of PRE(i) and its final value (0: no PRE)
+  double* scratch;                           // per-CTA scratch tile (refined solves)
+};
+
+// The whole chain of a HEAD task after its K-loop, out of line.  Pipelined path: newest k-tile into the shared tile,
+// four solve + SYRK blocks behind the panel flags of L_jj, X stored to T (and to the next owner's T) and
+// published, diagonal tile assembled in shared memory (ready for diag_factor_core).  When L_jj turns out
+// ill-conditioned (or with GPAR_HEAD_UNPIPELINED) the round-1 path: T completed in global memory, refined solve
+// through the inverse tile, X X^T out of shared memory, assembly.
+template <bool MULTI>
+__device__ __noinline__ void head_chain(unsigned char* smem_raw, const TaskCtx& h, const Peers* pe) {
+  GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
+  double* Xs = reinterpret_cast<double*>(smem_raw);
+  double* T = h.rowi + (int64_t)h.j * TILE;
+  const bool multi = MULTI && h.multi;
+  Acc acc;
+#ifndef GPAR_HEAD_UNPIPELINED
+  if (h.k1 > h.k1a) {
+    // the newest k-tile: T - L_{i,k1-1} L_{j,k1-1}^T goes straight into the shared tile (no global round trip)
+    acc_zero(acc);
+    gemm_nt_mainloop_dep<0>(stages, h.rowi + (int64_t)h.k1a * TILE, h.ldi, h.valid, h.rowj + (int64_t)h.k1a * TILE, h.lda, h.kb,
+                            TILE, acc, h.ready_i + h.k1a, h.ready_j + h.k1a, h.multi, T, h.ldi);
+    tile_sub_to_smem(Xs, T, h.ldi, h.valid, acc);
+    __syncthreads();
+  } else {
+    load_tile_to_smem(Xs, T, h.ldi, h.valid);
+  }
+  head_blocks(smem_raw, h.rowj + (int64_t)h.j * TILE, h.lda, h.Linv, acc, [&](int cb) {
+    if (multi) {
+      if (cb == 0) wait_ready(h.ready_j + h.j, true);
+    } else {
+      wait_ready(h.pfl + cb);
+    }
+  });
+  if (__ldcg(h.refine_flag) == 0.0) {
+    store_tile_from_smem(T, h.ldi, h.valid, Xs);
+    if (multi) store_tile_from_smem(peer_ptr(T, pe->delta[(pe->rank + 1) % pe->world]), h.ldi, h.valid, Xs);
+    fence_publish(pe);
+    __syncthreads();  // (also: every warp is done reading Xs)
+    if (threadIdx.x == 0) publish_flag(h.ready_ij, pe, PEERS_FIRST);
+    if (h.pre_parts > 0) wait_count(h.pre_count, h.pre_parts);  // every K-part of PRE(k) has been subtracted
+    assemble_diag(Xs, h.rowi + (int64_t)h.i * TILE, h.lda, h.valid, acc);
+    __syncthreads();
+    return;
+  }
+  // ill-conditioned L_jj: nothing has been stored or published.  The newest k-tile has to reach T in global memory.
+  __syncthreads();
+  if (h.k1 > h.k1a) {
+    acc_zero(acc);
+    gemm_nt_mainloop_dep<0>(stages, h.rowi + (int64_t)h.k1a * TILE, h.ldi, h.valid, h.rowj + (int64_t)h.k1a * TILE, h.lda, h.kb,
+                            TILE, acc, h.ready_i + h.k1a, h.ready_j + h.k1a, h.multi);
+    store_tile<1>(T, h.ldi, h.valid, h.kb, acc, false);
+    __threadfence();
+    __syncthreads();
+  }
+#endif
+  wait_ready(h.ready_j + h.j, multi);
+  const bool refine = __ldcg(h.refine_flag) != 0.0;
+  tile_solve(stages, T, h.ldi, h.valid, h.kb, h.Linv, h.rowj + (int64_t)h.j * TILE, h.lda, refine, h.scratch, acc);
+  if (multi) store_tile<0, true>(peer_ptr(T, pe->delta[(pe->rank + 1) % pe->world]), h.ldi, h.valid, h.kb, acc, false);
+  acc_to_smem(Xs, acc);  // the ring is idle: park X as the SYRK operand
+  fence_publish(pe);
+  __syncthreads();
+  if (threadIdx.x == 0) publish_flag(h.ready_ij, pe, PEERS_FIRST);
+  syrk_from_smem(Xs, acc);
+  if (h.pre_parts > 0) wait_count(h.pre_count, h.pre_parts);
+  __syncthreads();  // every warp is done reading Xs
+  assemble_diag(Xs, h.rowi + (int64_t)h.i * TILE, h.lda, h.valid, acc);
+  __syncthreads();
+}
+
 constexpr size_t DF_SMEM_BYTES = DIAG_SMEM_BYTES > GEMM_SMEM_BYTES ? DIAG_SMEM_BYTES : GEMM_SMEM_BYTES;
+static_assert(HEADP_SMEM_BYTES <= DF_SMEM_BYTES, "pipelined HEAD tiles must fit the dataflow kernel's shared memory");
 constexpr int DF_POOL_TILES = 192;  // scratch tiles for the persistent grid (>= SM count)
 
 struct DfArgs {
@@ -934,6 +1252,7 @@ struct DfArgs {
   int* ticket; int* ready;        // ready[(b * (nt + nbt) + i) * nt + j]
   int* pcount;                    // pcount[(b * (nt + nbt) + i) * nt + j]: K-parts already subtracted from tile (i, j)
                                   // (tile (k, k): parts of PRE(k))
+  int* pflag;                     // pflag[(b * nt + k) * 4 + p]: row panel p of L_kk / L_kk^-1 is out (single GPU)
   int grid;                       // CTAs of the launch (enters the split-K rule)
   long long* prof;                // debug: globaltimer stamps of HEAD(nt/2), HEAD(nt/2 + 1) (or null)
   Peers peers;                    // multi-GPU: rank, world and the peers' address deltas (world == 1: unused)
@@ -1047,9 +1366,6 @@ __host__ __device__ __forceinline__ void df_decode(int t, const DfShape& sh, int
   }
 }
 
-__device__ __forceinline__ void wait_count(const int* counter, int target) {
-  while (ld_acquire(counter) < target) __nanosleep(40);
-}
 
 // Per-CTA cycle accounting of the dataflow kernel (debug builds only: -DGPAR_DF_PROF, scripts/prof_budget.py):
 // thread 0 charges the cycles since its previous mark to a category; the counters land in
@@ -1078,7 +1394,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
   }
 #endif
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
-  double* Xs = reinterpret_cast<double*>(smem_raw);  // HEAD: operand tile, then the diagonal-factor tile
   const int tid = threadIdx.x;
   if (tid == 0) s_peers = p.peers;
   const bool multi = MULTI && p.peers.world > 1;  // MULTI = false: all peer code compiles out
@@ -1112,7 +1427,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
     if (kind == TASK_D0) {
       const int kb = static_cast<int>(min64(TILE, p.n));
       diag_load(smem_raw, Ab, p.lda, kb);
-      diag_factor_core<MULTI>(smem_raw, Ab, p.lda, kb, 0, wsb, flags, p.info + b, ready_b, pe, nullptr);
+      diag_factor_core<MULTI>(smem_raw, Ab, p.lda, kb, 0, wsb, flags, p.info + b, ready_b, pe, nullptr,
+                              MULTI ? nullptr : p.pflag + (int64_t)b * p.nt * 4);
       DFP_MARK(11);
     } else {
       // PRE (k): A_kk -= sum_{l<k-1} L_kl L_kl^T.  PLAIN (i, j) and HEAD (k = i, j = k - 1): T = A_ij - sum_{l<j}
@@ -1138,21 +1454,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
       const int* ready_j = ready_b + (int64_t)j * p.nt;
       double* T = rowi + (int64_t)j * TILE;
       int* pcount = p.pcount + ((int64_t)b * rows_total + i) * p.nt + j;
-      Acc acc;
-      if (k1 > k0) {
+      const bool head = kind == TASK_HEAD && part + 1 == nparts;  // (the last K-part of its tile is the HEAD itself)
+#ifndef GPAR_HEAD_UNPIPELINED
+      // A pipelined HEAD keeps the newest k-tile (the one that needs L_{k,k-1}, published by the HEAD of the previous
+      // column a moment ago) out of this K-loop: it is applied last, straight into the shared tile (head_chain).
+      const int k1a = (head && k1 > k0) ? k1 - 1 : k1;
+#else
+      const int k1a = k1;
+#endif
+      if (k1a > k0) {
+        Acc acc;
         acc_zero(acc);
-        // (the masked lower-triangular MODE 1 path is slower than the full tile: its branches break
-        //  the DMMA/LDS software pipeline; measured 2x per chunk)
+        // (the 8 x 32 masks of MODE 1 are slower than the full tile: their branches break the DMMA / LDS software
+        //  pipeline; MODE 3 drops the upper-right 64 x 64 quadrant of a diagonal tile with straight-line bodies)
 #ifndef GPAR_PRE_FULL
-        if (pre && valid == TILE)  // diagonal tile: only col <= row is stored -- skip the upper-right 64 x 64 quadrant
+        if (pre && valid == TILE)
           gemm_nt_mainloop_dep<3>(stages, rowi + (int64_t)k0 * TILE, ldi, valid, rowj + (int64_t)k0 * TILE, p.lda, kb,
-                                  (k1 - k0) * TILE, acc, ready_i + k0, ready_j + k0, multi, T, ldi);
+                                  (k1a - k0) * TILE, acc, ready_i + k0, ready_j + k0, multi, T, ldi);
         else
 #endif
         gemm_nt_mainloop_dep<0>(stages, rowi + (int64_t)k0 * TILE, ldi, valid, rowj + (int64_t)k0 * TILE, p.lda, kb,
-                                (k1 - k0) * TILE, acc, ready_i + k0, ready_j + k0, multi, T, ldi);
+                                (k1a - k0) * TILE, acc, ready_i + k0, ready_j + k0, multi, T, ldi);
         DFP_MARK(1);
-        DFP_ADD(13, k1 - k0);
+        DFP_ADD(13, k1a - k0);
         if (part > 0) wait_count(pcount, part);  // parts subtract in order: the rounding does not depend on timing
         store_tile<1>(T, ldi, valid, kb, acc, pre);
         __threadfence();
@@ -1166,46 +1490,55 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
         continue;
       }
       if (pf) pf[1] = globaltimer_ns();
-      wait_ready(ready_j + j, multi);
-      DFP_MARK(4);
-      if (pf) pf[2] = globaltimer_ns();
-      const bool refine = __ldcg(flags + j) != 0.0;
-      tile_solve(stages, T, ldi, valid, kb, wsb + (int64_t)j * TILE * TILE, rowj + (int64_t)j * TILE, p.lda, refine,
-                 scratch, acc);
-      DFP_MARK(5);
-      // multi-GPU: L_ij goes into the peers' copies of the matrix by NVLink stores straight from the
-      // accumulators -- first to the rank that owns the next tile row (+ flags), then to the others
-      // (a HEAD defers them until its diagonal tile is out: they are off the critical chain).
-      if (multi) store_tile<0, true>(peer_ptr(T, p.peers.delta[(p.peers.rank + 1) % p.peers.world]), ldi, valid, kb, acc, false);
-      if (kind == TASK_HEAD) acc_to_smem(Xs, acc);  // the ring is idle: park X as the SYRK operand
-      fence_publish(pe);
-      __syncthreads();
-      if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe, PEERS_FIRST);
-      if (multi && p.peers.world > 2 && kind != TASK_HEAD) {
-        for (int pr = 0; pr < p.peers.world; ++pr)
-          if (peer_in_set(pe, pr, PEERS_REST)) store_tile<0, true>(peer_ptr(T, p.peers.delta[pr]), ldi, valid, kb, acc, false);
-        __threadfence_system();
+      if (head) {
+        // The chain of column j -> j + 1 (head_chain, out of line): ends with the diagonal tile assembled in shared
+        // memory.  With several GPUs there are no panel flags: the same arithmetic (the factor stays bit-identical
+        // to the single-GPU one) behind the tile's ready flag.
+        TaskCtx c;
+        c.rowi = rowi; c.ldi = ldi; c.valid = valid; c.rowj = rowj; c.lda = p.lda; c.kb = kb;
+        c.i = i; c.j = j; c.k0 = k0; c.k1a = k1a; c.k1 = k1; c.part = part;
+        c.pre = false; c.head = true; c.multi = multi;
+        c.ready_i = ready_i; c.ready_j = ready_j; c.ready_ij = ready_b + (int64_t)i * p.nt + j; c.pcount = pcount;
+        c.pfl = p.pflag + ((int64_t)b * p.nt + j) * 4;
+        c.Linv = wsb + (int64_t)j * TILE * TILE; c.refine_flag = flags + j;
+        c.pre_count = p.pcount + ((int64_t)b * rows_total + i) * p.nt + i;
+        c.pre_parts = (i >= 2) ? df_split(sh, i - 2) : 0;  // PRE(i) is ticketed in column group i - 2
+        c.scratch = scratch;
+        head_chain<MULTI>(smem_raw, c, pe);
+        DFP_ADD(13, k1 - k1a);
+        DFP_MARK(5);
+        if (pf) pf[2] = pf[3] = pf[4] = globaltimer_ns();
+      } else {
+        Acc acc;
+        wait_ready(ready_j + j, multi);
+        DFP_MARK(4);
+        const bool refine = __ldcg(flags + j) != 0.0;
+        tile_solve(stages, T, ldi, valid, kb, wsb + (int64_t)j * TILE * TILE, rowj + (int64_t)j * TILE, p.lda, refine,
+                   scratch, acc);
+        DFP_MARK(5);
+        // multi-GPU: L_ij goes into the peers' copies of the matrix by NVLink stores straight from the
+        // accumulators -- first to the rank that owns the next tile row (+ flags), then to the others
+        if (multi) store_tile<0, true>(peer_ptr(T, p.peers.delta[(p.peers.rank + 1) % p.peers.world]), ldi, valid, kb, acc, false);
+        fence_publish(pe);
         __syncthreads();
-        if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe, PEERS_REST);
+        if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe, PEERS_FIRST);
+        if (multi && p.peers.world > 2) {
+          for (int pr = 0; pr < p.peers.world; ++pr)
+            if (peer_in_set(pe, pr, PEERS_REST)) store_tile<0, true>(peer_ptr(T, p.peers.delta[pr]), ldi, valid, kb, acc, false);
+          __threadfence_system();
+          __syncthreads();
+          if (tid == 0) publish_flag(ready_b + (int64_t)i * p.nt + j, pe, PEERS_REST);
+        }
+        DFP_MARK(6);
       }
-      if (pf) pf[3] = globaltimer_ns();
-      DFP_MARK(6);
-      if (kind == TASK_HEAD) {
+      if (head) {
         const int k = i;
-        syrk_from_smem(Xs, acc);
-        DFP_MARK(7);
-        if (pf) pf[4] = globaltimer_ns();
-        if (k >= 2)  // every K-part of PRE(k) (ticketed in column group k - 2) has been subtracted
-          wait_count(p.pcount + ((int64_t)b * rows_total + k) * p.nt + k, df_split(sh, k - 2));
-        DFP_MARK(8);
-        __syncthreads();  // every warp is done reading Xs
         double* Tkk = rowi + (int64_t)k * TILE;
-        assemble_diag(Xs, Tkk, p.lda, valid, acc);
-        __syncthreads();
         DFP_MARK(9);
         if (pf) pf[5] = globaltimer_ns();
         diag_factor_core<MULTI>(smem_raw, Tkk, p.lda, valid, (int64_t)k * TILE, wsb + (int64_t)k * TILE * TILE, flags + k,
-                         p.info + b, ready_b + (int64_t)k * p.nt + k, pe, nullptr);
+                         p.info + b, ready_b + (int64_t)k * p.nt + k, pe, nullptr,
+                         MULTI ? nullptr : p.pflag + ((int64_t)b * p.nt + k) * 4);
         DFP_MARK(10);
 #ifdef GPAR_DF_PROF
         if (threadIdx.x == 0 && p.prof && b == 0 && k < 1024) p.prof[64 + 16 * 256 + k] = globaltimer_ns();
@@ -1323,7 +1656,7 @@ static int64_t ws_stride(int64_t nt, int64_t nbt) { return ws_scratch_off(nt) + 
 
 // After the per-matrix regions: [DF_POOL_TILES scratch tiles][int region: ticket (2 ints) + ready flags].
 static int64_t ws_ready_ints(int64_t nt, int64_t nbt, int64_t batch) {
-  return 2 + 2 * batch * (nt + nbt) * nt;  // ticket, tile ready flags, tile K-part counters
+  return 2 + 2 * batch * (nt + nbt) * nt + 4 * batch * nt;  // ticket, tile ready flags, K-part counters, panel flags
 }
 
 extern "C" size_t gpar_potrf_workspace_bytes(int64_t n, int64_t nb, int64_t batch) {
@@ -1381,6 +1714,7 @@ static int launch_dataflow(double* A, int64_t lda, int64_t n, int64_t strideA, d
   int* ints = reinterpret_cast<int*>(p.pool + (int64_t)DF_POOL_TILES * TILE * TILE);
   p.ticket = ints; p.ready = ints + 2;
   p.pcount = p.ready + batch * (int64_t)(nt + nbt) * nt;
+  p.pflag = p.pcount + batch * (int64_t)(nt + nbt) * nt;
   if (reset) df_reset(ws, n, nb, batch, stream);
   if ((long long)grid > total) grid = (int)total;  // (p.grid keeps the nominal size: it only feeds the split rule)
   if (peers.world > 1)
