@@ -164,10 +164,18 @@ def _stack(eng, mats, spare=0):
 
 
 def _cat(eng, vecs):
+    """Concatenate device vectors (own copy kernel; torch only allocates)."""
     vecs = [v for v in vecs if v is not None and v.numel() > 0]
     if not vecs:
         return eng.zeros(1)
-    return vecs[0] if len(vecs) == 1 else torch.cat(vecs)
+    if len(vecs) == 1:
+        return vecs[0]
+    out = eng.empty(sum(int(v.numel()) for v in vecs))
+    off = 0
+    for v in vecs:
+        eng.gather_rows(v, 1, None, int(v.numel()), 1, out, 1, dst_off=off)
+        off += int(v.numel())
+    return out
 
 
 _default_engine = None
@@ -485,7 +493,7 @@ class GPAR:
                 elif layer.block is not None:
                     blk = layer.block
                     X = _stack(eng, [blk.X, xs])
-                    fac = Factor(eng, layer.spec, X.t, X.ld, torch.cat([blk.d, d_s[:ns]]), blk.y, blk.n, ns)
+                    fac = Factor(eng, layer.spec, X.t, X.ld, _cat(eng, [blk.d, d_s[:ns]]), blk.y, blk.n, ns)
                     fac.n_blk, fac.n_a = blk.n, 0
                 else:
                     fac = Factor(eng, layer.spec, xs.t, xs.ld, d_s, eng.zeros(1), 0, ns)

@@ -374,7 +374,7 @@ def logpdf_sparse(gpar, x, y, w, only_last_layer, return_inputs, x_ind, outputs,
         return xd, zd
     total = 0.0
     if slots:
-        vals = torch.stack([s for s, _ in slots]).cpu().numpy()
+        vals = np.stack([s.cpu().numpy() for s, _ in slots])  # (device -> host reads of 4 doubles per layer)
         for (t0, t1, t2, _), (_, n) in zip(vals, slots):
             if n > 0:
                 total += -0.5 * (t0 + t1 - t2)

@@ -15,7 +15,10 @@ from gpar_b200 import _lib  # noqa: E402
 
 D0, HEAD, PLAIN, PRE = 0, 1, 2, 3
 DEFAULT = dict(kt=17.72, kt_y=4.0, epi=8.0, solve=14.0, ticket=0.6, syrk=11.4, asm=3.8, fac_flag=28.0, fac_rest=5.0,
-               d0=36.0, refill=1.5, poll=0.2)
+               d0=36.0, refill=1.5, poll=0.2,
+               # pipelined HEAD (round 2; pipelined=1): newest k-tile applied on chip, four solve + SYRK blocks behind
+               # the panel flags of the previous diagonal tile, which go up fac_panel us apart
+               pipelined=1.0, newest=22.0, block=7.5, publish=3.0, fac_panel=9.0)
 
 
 def tickets(n, nb, batch, grid):
@@ -44,14 +47,18 @@ def simulate(n, nb=1, grid=148, P=None, verbose=False):
     def task(kind, i, j, part, nparts):
         yield ("delay", P["ticket"])
         if kind == D0:
-            yield ("delay", P["d0"])
+            for cb in range(4):
+                yield ("delay", P["d0"] / 4)
+                yield ("set", ("pf", 0, cb))
             yield ("set", ("r", 0, 0))
             return
         pre = kind == PRE
         nk = i - 1 if pre else j
         k0, k1 = part * nk // nparts, (part + 1) * nk // nparts
         kt = P["kt"] if i < nt else P["kt_y"]
-        for k in range(k0, k1):
+        piped = P["pipelined"] > 0 and kind == HEAD and part + 1 == nparts
+        k1a = k1 - 1 if (piped and k1 > k0) else k1
+        for k in range(k0, k1a):
             stalled = False
             for key in ((("r", i, k),) if pre else (("r", i, k), ("r", j, k))):
                 if key not in flags:
@@ -62,10 +69,34 @@ def simulate(n, nb=1, grid=148, P=None, verbose=False):
             key = ("pc", i, j, part - 1)
             if key not in flags:
                 yield ("wait", key)
-        if k1 > k0:
+        if k1a > k0:
             yield ("delay", P["epi"])
         if pre or part + 1 < nparts:
             yield ("set", ("pc", i, j, part))
+            return
+        if piped:
+            if k1 > k1a:
+                for key in (("r", i, k1a), ("r", j, k1a)):
+                    if key not in flags:
+                        yield ("wait", key)
+                yield ("delay", P["newest"])
+            for cb in range(4):
+                key = ("pf", j, cb)
+                if key not in flags:
+                    yield ("wait", key)
+                yield ("delay", P["block"])
+            yield ("delay", P["publish"])
+            yield ("set", ("r", i, j))
+            k = i
+            if k >= 2 and ("pcall", k) not in flags:
+                yield ("wait", ("pcall", k))
+            yield ("delay", P["asm"])
+            for cb in range(3):
+                yield ("delay", P["fac_panel"])
+                yield ("set", ("pf", k, cb))
+            yield ("delay", P["fac_panel"])
+            yield ("set", ("pf", k, 3))
+            yield ("set", ("r", k, k))
             return
         if ("r", j, j) not in flags:
             yield ("wait", ("r", j, j))
