@@ -75,7 +75,8 @@ def test_gram_cross(eng, nx, ny):
     assert np.max(np.abs(got - ref)) <= 4e-14 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("n,nb", [(1, 0), (31, 1), (128, 3), (129, 0), (300, 130), (777, 1), (1024, 64)])
+@pytest.mark.parametrize("n,nb", [(1, 0), (31, 1), (128, 3), (129, 0), (257, 0), (300, 130), (385, 1), (777, 1), (1024, 64),
+                                  (1153, 70), (2049, 1), (3500, 1)])
 def test_potrf_with_appended_rows(eng, n, nb):
     rng = np.random.default_rng(n + nb)
     A = spd(n, rng)
@@ -134,6 +135,46 @@ def test_potrf_near_singular_matches_lapack(eng):
     L = np.tril(Ad.cpu().numpy().reshape(N, ld)[:, :N])
     Lref = sla.cholesky(K, lower=True)
     assert np.abs(L @ L.T - K).max() <= 20 * np.abs(Lref @ Lref.T - K).max() + 1e-15
+
+
+def test_potrf_near_singular_interior_tiles(eng):
+    """Ill-conditioned diagonal tiles in the interior of the sweep (rows 256..639 are a tight cluster with noise
+    1e-9: kappa_inf(L_kk) >> 1e3 for tile 2; the Schur complements of tiles 3, 4 are noise-dominated): the pipelined HEAD
+    task of column 3 finds the refine flag set after its four blocks, pushes its newest k-tile to global memory and
+    falls back to the refined solve
+    (potrf.cu head_chain).  Backward error at LAPACK's level."""
+    rng = np.random.default_rng(3)
+    n = 1300
+    X = rng.uniform(0, 1, (n, 2))
+    d = rng.uniform(0.05, 0.2, n)
+    X[256:640] = X[256] + 2e-3 * rng.uniform(-1, 1, (384, 2))
+    d[256:640] = 1e-9
+    K = O.kernel_matrix([dict(type="eq", variance=1.0, cols=[0, 1], scales=[0.25, 0.25])], X, X) + np.diag(d)
+    ld = n
+    Ap = np.zeros((n, ld)); Ap[:, :n] = np.tril(K)
+    Ad = dev(eng, Ap).reshape(-1)
+    ws, info = eng.potrf(Ad, ld, n)
+    assert int(info.cpu()[0]) == 0
+    nt = (n + 127) // 128
+    flags = ws.cpu().numpy()[nt * 128 * 128 : nt * 128 * 128 + nt]
+    assert flags[2] != 0 and not flags[:2].any()  # the refined path really ran (HEAD of column 3), the plain one too
+    L = np.tril(Ad.cpu().numpy().reshape(n, ld)[:, :n])
+    Lref = sla.cholesky(K, lower=True)
+    assert np.abs(L @ L.T - K).max() <= 20 * np.abs(Lref @ Lref.T - K).max() + 1e-15
+
+
+def test_potrf_batched_multi_tile(eng):
+    """Batched factorisation of multi-tile matrices (panel flags are per matrix and per diagonal tile)."""
+    rng = np.random.default_rng(8)
+    n, batch = 700, 3
+    mats = [spd(n, rng, cond_noise=0.05 * (b + 1)) for b in range(batch)]
+    Ad = dev(eng, np.stack([np.tril(a) for a in mats])).reshape(-1)
+    _, info = eng.potrf(Ad, n, n, batch=batch, strideA=n * n)
+    assert np.all(info.cpu().numpy() == 0)
+    got = Ad.cpu().numpy().reshape(batch, n, n)
+    for b in range(batch):
+        Lref = sla.cholesky(mats[b], lower=True)
+        assert np.linalg.norm(np.tril(got[b]) - Lref) / np.linalg.norm(Lref) <= 1e-11
 
 
 def test_potrf_batched(eng):
