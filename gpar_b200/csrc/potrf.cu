@@ -1041,6 +1041,34 @@ __device__ __forceinline__ void tile_sub_to_smem(double* __restrict__ Ts, const 
   }
 }
 
+// acc = -T (global tile, rows x 128; zeros beyond `rows`), accumulator layout of MODE 0.
+__device__ __forceinline__ void acc_load_neg(Acc& acc, const double* __restrict__ T, int64_t ldt, int rows) {
+  const int warp = canonical_warp(), lane = threadIdx.x & 31;
+  const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = acc_row(wm, i) + gid;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double2 v = (r < rows) ? __ldcg(reinterpret_cast<const double2*>(T + (int64_t)r * ldt + wn * 64 + j * 8 + 2 * tig))
+                                   : make_double2(0.0, 0.0);
+      acc[i][j][0] = -v.x;
+      acc[i][j][1] = -v.y;
+    }
+  }
+}
+// Ts (shared) = -acc.
+__device__ __forceinline__ void acc_neg_to_smem(double* __restrict__ Ts, const Acc& acc) {
+  const int warp = canonical_warp(), lane = threadIdx.x & 31;
+  const int wm = warp & 3, wn = warp >> 2, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<double2*>(Ts + (acc_row(wm, i) + gid) * DLD + wn * 64 + j * 8 + 2 * tig) =
+          make_double2(-acc[i][j][0], -acc[i][j][1]);
+}
+
 // The four blocks.  Ts holds T on entry and X on return; S (zeroed here) holds the lower part of X X^T.
 // Ljj: tile (j, j) of the matrix (global, ld ldl); Linv: its inverse tile (global, ld 128).
 // wait_panel(cb) blocks until row panel cb of both is in global memory.
@@ -1185,11 +1213,13 @@ __device__ __noinline__ void head_chain(unsigned char* smem_raw, const TaskCtx& 
   Acc acc;
 #ifndef GPAR_HEAD_UNPIPELINED
   if (h.k1 > h.k1a) {
-    // the newest k-tile: T - L_{i,k1-1} L_{j,k1-1}^T goes straight into the shared tile (no global round trip)
-    acc_zero(acc);
+    // the newest k-tile: T - L_{i,k1-1} L_{j,k1-1}^T goes straight into the shared tile (no global round trip).  The
+    // accumulators start at -T (loaded before the wait for L_{j,k1-1}: off the chain), so that what is left after
+    // the K = 128 loop is a negation on the way into shared memory.
+    acc_load_neg(acc, T, h.ldi, h.valid);
     gemm_nt_mainloop_dep<0>(stages, h.rowi + (int64_t)h.k1a * TILE, h.ldi, h.valid, h.rowj + (int64_t)h.k1a * TILE, h.lda, h.kb,
-                            TILE, acc, h.ready_i + h.k1a, h.ready_j + h.k1a, h.multi, T, h.ldi);
-    tile_sub_to_smem(Xs, T, h.ldi, h.valid, acc);
+                            TILE, acc, h.ready_i + h.k1a, h.ready_j + h.k1a, h.multi);
+    acc_neg_to_smem(Xs, acc);
     __syncthreads();
   } else {
     load_tile_to_smem(Xs, T, h.ldi, h.valid);
