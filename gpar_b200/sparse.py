@@ -77,7 +77,8 @@ class SparseFactor:
         # A = I + C^T C with C = diag(sigma^-1/2) B^T, formed as an NT SYRK on C^T (M x n)
         ldn = _even(max(n, 2))
         self.JA = eng.zeros(M * ldz)
-        eng.scatter_col(self.JA, ldz + 1, 0, None, eng.to_device(np.ones(M)), M)  # identity: stride ld + 1
+        # identity (+ the jitter every reference Cholesky carries, matrix.cholesky): diagonal = stride ld + 1
+        eng.scatter_col(self.JA, ldz + 1, 0, None, eng.to_device(np.full(M, 1.0 + eng.epsilon)), M)
         self.c = eng.zeros(ldz)
         self.terms = eng.zeros(4)  # [row terms, logdet A, |v|^2]
         if n:

@@ -411,7 +411,7 @@ class PseudoObs:
             L_z = _chol(f.kernel(z, z))
             Bm = _solve_lower(L_z, f.kernel(z, x))  # (M, n)
             A = np.eye(z.shape[0]) + (Bm / sig[None, :]) @ Bm.T
-            L_A = sla.cholesky(A, lower=True, check_finite=False)
+            L_A = _chol(A)  # matrix.cholesky(Dense) adds B.epsilon to every factorisation [UPSTREAM-RECALL]
             ybar = self.y - f.mean(x)
             c = Bm @ (ybar / sig[:, None])  # L_z^-1 K_zx Sigma^-1 ybar
             LA_inv_c = _solve_lower(L_A, c)
