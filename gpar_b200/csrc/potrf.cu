@@ -393,7 +393,11 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
   const bool multi = MULTI && (pe != nullptr) && (pe->world > 1);  // MULTI = false: all peer code compiles out
   if (tid == 0) s_int[0] = 0;
   if (tid < TILE) rowL[tid] = 0.0;
-  const bool panelwise = !multi && (panel_flags != nullptr);
+  // Panel-wise write-out of the LOCAL copy (also with several GPUs: the HEAD of the next column usually lives on
+  // this rank -- tile rows are dealt in blocks of row_block -- and pipelines behind the local panel flags; the
+  // peers get the finished tile and the ready flag at the end, as before).
+  const bool panelwise = panel_flags != nullptr;
+  const bool panel_end = panelwise && !multi;  // single GPU: the last panel is written the same way, no peer pass
   if (panelwise)
     for (int q = tid; q < 8 * TILE; q += 256) isumP[q] = 0.0;
   const bool vec_l = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(Atile) & 15) == 0);
@@ -520,12 +524,12 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
       for (int rb = 0; rb < 4; ++rb) LT[warp * TILE + 32 * rb + lane] = isum[rb];
     }
   };
-  if (panelwise) write_panel(TILE / PANEL - 1, 0, 8); else write_linv(PEERS_FIRST);
+  if (panel_end) write_panel(TILE / PANEL - 1, 0, 8); else write_linv(PEERS_FIRST);
   GPAR_PROF(14);
   __syncthreads();
   if (tid < TILE) {
     double s = 0.0;
-    const double* part = panelwise ? isumP : LT;
+    const double* part = panel_end ? isumP : LT;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += (tid < kb) ? part[w * TILE + tid] : 0.0;
 #pragma unroll
@@ -549,7 +553,7 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
   fence_publish(pe);
   __syncthreads();
   const bool refine = s_int[1] != 0;
-  if (panelwise) {  // every row panel of L and Linv is out (the last one just now), the refine flag is set
+  if (panel_end) {  // every row panel of L and Linv is out (the last one just now), the refine flag is set
     if (tid == 0) {
       st_release(panel_flags + (TILE / PANEL - 1), 1);
       if (ready_flag) st_release(ready_flag, 1);
@@ -598,6 +602,11 @@ __device__ __noinline__ void diag_factor_core(unsigned char* smem_raw, double* _
     fence_publish(pe);
     __syncthreads();
     if (tid == 0) publish_flag(ready_flag, pe, early ? PEERS_REST : PEERS_ALL);
+  }
+  if (panelwise) {  // (several GPUs) the local copy is complete: last local panel flag
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release(panel_flags + (TILE / PANEL - 1), 1);
   }
   GPAR_PROF(12);
 #undef GPAR_PROF
@@ -1224,8 +1233,11 @@ __device__ __noinline__ void head_chain(unsigned char* smem_raw, const TaskCtx& 
   } else {
     load_tile_to_smem(Xs, T, h.ldi, h.valid);
   }
+  // several GPUs: panel flags exist on the rank that factored L_jj only; behind a remote factor the blocks wait
+  // for the tile's (pushed) ready flag -- same arithmetic either way
+  const bool remote = multi && ((h.j / pe->row_block) % pe->world) != pe->rank;
   head_blocks(smem_raw, h.rowj + (int64_t)h.j * TILE, h.lda, h.Linv, acc, [&](int cb) {
-    if (multi) {
+    if (remote) {
       if (cb == 0) wait_ready(h.ready_j + h.j, true);
     } else {
       wait_ready(h.pfl + cb);
@@ -1458,7 +1470,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
       const int kb = static_cast<int>(min64(TILE, p.n));
       diag_load(smem_raw, Ab, p.lda, kb);
       diag_factor_core<MULTI>(smem_raw, Ab, p.lda, kb, 0, wsb, flags, p.info + b, ready_b, pe, nullptr,
-                              MULTI ? nullptr : p.pflag + (int64_t)b * p.nt * 4);
+                              p.pflag + (int64_t)b * p.nt * 4);
       DFP_MARK(11);
     } else {
       // PRE (k): A_kk -= sum_{l<k-1} L_kl L_kl^T.  PLAIN (i, j) and HEAD (k = i, j = k - 1): T = A_ij - sum_{l<j}
@@ -1568,7 +1580,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_dataflow_kernel(const D
         if (pf) pf[5] = globaltimer_ns();
         diag_factor_core<MULTI>(smem_raw, Tkk, p.lda, valid, (int64_t)k * TILE, wsb + (int64_t)k * TILE * TILE, flags + k,
                          p.info + b, ready_b + (int64_t)k * p.nt + k, pe, nullptr,
-                         MULTI ? nullptr : p.pflag + ((int64_t)b * p.nt + k) * 4);
+                         p.pflag + ((int64_t)b * p.nt + k) * 4);
         DFP_MARK(10);
 #ifdef GPAR_DF_PROF
         if (threadIdx.x == 0 && p.prof && b == 0 && k < 1024) p.prof[64 + 16 * 256 + k] = globaltimer_ns();
