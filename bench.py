@@ -177,6 +177,20 @@ def _cpu_dgemm_rate():
     return 2.0 * 2048 ** 3 / max(time.perf_counter() - t0, 1e-6)
 
 
+def _cpu_entry_time():
+    """Seconds per matrix entry of one elementwise fp64 pass with an `exp` (best of three on 4096^2): the Gram
+    build of a reference layer costs about a dozen such passes (distances, exp, products, sums, the noise add)."""
+    import torch
+
+    a = torch.rand(4096, 4096, dtype=torch.float64)
+    best = 1.0
+    for _ in range(4):
+        t0 = time.perf_counter()
+        torch.exp(a)
+        best = min(best, time.perf_counter() - t0)
+    return best / a.numel()
+
+
 def reference_step(data, data_kw, reg_kw, budget_s):
     """One (condition, logpdf, predict) pass of the reference op sequence at the FULL configuration:
     full-n logpdf, full-n conditioning, then the S chains one after the other (every chain at full n, n*)
@@ -195,13 +209,18 @@ def reference_step(data, data_kw, reg_kw, budget_s):
     S, n, p, ns = data_kw["S"], data_kw["n"], data_kw["p"], data_kw["ns"]
     rate = _cpu_dgemm_rate()
     replace = bool(reg_kw.get("replace", False))
-    pred_layer = 1.4 * (n ** 3 / 3.0 + (float(n) ** 3 if replace else 0.0) + 40.0 * n * n) / rate
+    pred_layer = (1.4 * (n ** 3 / 3.0 + (float(n) ** 3 if replace else 0.0)) / rate
+                  + 12.0 * _cpu_entry_time() * float(n) ** 2)
     pred_chain = 1.4 * p * 3.0 * float(n) ** 2 * ns / rate
     need = 1.7 * p * 8.0 * n * n  # p cached factors of the conditioned model + Gram temporaries
     avail = float(psutil.virtual_memory().available)
     detail = {"host_mem_available_gb": avail / 1e9, "host_dgemm_gflops": rate / 1e9,
               "predicted_fixed_s": 2 * p * pred_layer, "predicted_chain_s": pred_chain}
-    if need < 0.7 * avail and 2 * p * pred_layer + pred_chain < budget_s:
+    # the full path needs the factors in host memory, its fixed part plus one chain inside the budget, and a
+    # whole step (all S chains) that is not hopelessly beyond it: C3 is ~340 s on 16 cores and runs in full;
+    # C5 is ~9 hours, so nothing near a full pass can be measured and a shorter bounded sample says as much
+    if (need < 0.7 * avail and 2 * p * pred_layer + pred_chain < budget_s
+            and 2 * p * pred_layer + S * pred_chain < 2.0 * budget_s):
         r = timed_step(reg_kw, data, S, device="cpu", budget_s=budget_s)
         t_fixed = r["t_logpdf"] + r["t_condition"]
         full = r["chains"] == S
@@ -210,6 +229,8 @@ def reference_step(data, data_kw, reg_kw, budget_s):
                       t_chain_mean_s=r["t_chain_mean"], t_measured_s=r["t_total"], extrapolated=not full,
                       logpdf=r["logpdf"], _mean=r["mean"])
         return t_full, detail
+    budget_s = min(budget_s, float(os.environ.get("GPAR_REF_BOUNDED_BUDGET_S", 300.0)))
+    detail["bounded_budget_s"] = budget_s
     t_start = time.perf_counter()
     done = []
 
