@@ -456,7 +456,7 @@ def measure_trsm_rows_kernel(eng, peaks, n, nb):
     flops = float(nb) * float(n) ** 2
     ach = flops / avg / 1e12
     traffic, tsrc = _ncu_traffic("trsm_rows_kernel")
-    return {"kernel": "trsm_rows_kernel (B <- B L^-T, DMMA m8n8k4, one 128-row tile of B per CTA)", "bound": "tensor",
+    return {"kernel": "trsm_rows_kernel (B <- B L^-T, DMMA m8n8k4, one row block of B per CTA: whole waves of 128 rows + a tail wave of 32 / 64 / 96-row blocks)", "bound": "tensor",
             "achieved": ach, "peak": peaks["dgemm_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["dgemm_tflops"],
             "traffic": traffic, "traffic_source": tsrc, "launch_ms": avg * 1e3, "algorithmic_flops": flops,
             "algorithmic_bytes": 8.0 * (n * (n + 1) / 2 + 2.0 * nb * n),

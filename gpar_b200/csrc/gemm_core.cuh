@@ -63,7 +63,7 @@ __device__ __forceinline__ void load_chunk(GemmStage& st, const double* __restri
 
 // Warp (wm, wn) owns the 8-row groups {(4 i + wm) * 8} (interleaved over the four m-warps, so that
 // triangular tiles load all four SM sub-partitions evenly) and the columns wn*64 + j*8.
-// MODE 0: full tile.  MODE 1: lower-triangular OUTPUT (SYRK on a diagonal tile): 8x8 sub-tiles
+// MODE 0: full tile (MODE 4: the same with straight-line bodies for 32 / 64 / 96 valid rows).  MODE 1: lower-triangular OUTPUT (SYRK on a diagonal tile): 8x8 sub-tiles
 // strictly above the diagonal are skipped.  MODE 2: lower-triangular B OPERAND (B[c][k] = 0 for
 // k > c, i.e. X Linv^T / X L^T): k-chunks that only meet zeros are skipped, and the accumulator
 // columns are PERMUTED (acc_col<true>): every consumer of a MODE 2 result passes PERM = true.  Row
@@ -130,6 +130,23 @@ __device__ __forceinline__ void mma_tri_steps(const GemmStage& st, Acc& acc, int
   }
 }
 
+// MODE 4 bodies: the first NI row groups of every warp, all 8 column tiles.
+template <int NI>
+__device__ __forceinline__ void mma_rows_steps(const GemmStage& st, Acc& acc, int wm, int wn, int gid, int tig) {
+#pragma unroll
+  for (int kk = 0; kk < BK; kk += 4) {
+    double a[NI], b[8];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) a[i] = st.a[(acc_row(wm, i) + gid) * LDSM + kk + tig];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = st.b[(wn * 64 + j * 8 + gid) * LDSM + kk + tig];
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void mma_chunk(const GemmStage& st, Acc& acc, int wm, int wn, int gid, int tig, int k0,
                                           unsigned mask) {
@@ -154,6 +171,17 @@ __device__ __forceinline__ void mma_chunk(const GemmStage& st, Acc& acc, int wm,
     return;
   }
   if (mask == 0) return;
+  if (MODE == 4) {
+    // row blocks of 32 / 64 / 96 / 128 rows (trsm_rows_kernel's tail blocks): the interleaved row groups
+    // keep all eight warps busy with 1 .. 4 groups each; one uniform switch selects a straight-line body
+    switch (mask) {
+      case 0x03u: mma_rows_steps<1>(st, acc, wm, wn, gid, tig); return;
+      case 0x0Fu: mma_rows_steps<2>(st, acc, wm, wn, gid, tig); return;
+      case 0x3Fu: mma_rows_steps<3>(st, acc, wm, wn, gid, tig); return;
+      case 0xFFu: mma_rows_steps<4>(st, acc, wm, wn, gid, tig); return;
+      default: break;  // ragged last block: the per-block branches below
+    }
+  }
 #pragma unroll
   for (int kk = 0; kk < BK; kk += 4) {
     double a[4], b[8];

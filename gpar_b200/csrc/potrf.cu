@@ -748,15 +748,43 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_sub_kernel(const SubArgs
 // B (nb x n) <- B L^-T with L already factored: every CTA owns one 128-row tile of B and sweeps
 // the column tiles left to right (left-looking), so no inter-CTA dependency exists.
 // --------------------------------------------------------------------------------------
+// Row blocks: whole waves of 128-row blocks (one CTA per SM), then the rows that are left as blocks of
+// 32 / 64 / 96 rows -- the smallest height that still fits them in ONE more wave -- instead of a last wave of
+// 128-row blocks that leaves most SMs idle (C5 on 8 GPUs: 512 blocks = 3.46 waves -> 3 waves + 136 blocks of
+// 64 rows).  Rows are independent, so the partition changes no bit of the result.
+struct RowPlan {
+  int64_t full_blocks;  // 128-row blocks [0, full_blocks)
+  int64_t tail_blocks;  // then blocks of tail_h rows
+  int tail_h;
+};
+__host__ __device__ inline RowPlan trsm_row_plan(int64_t nb, int sms) {
+  RowPlan p;
+  const int64_t T = (nb + TILE - 1) / TILE;
+  const int64_t r = T % sms;
+  p.full_blocks = T - r;
+  p.tail_blocks = 0;
+  p.tail_h = TILE;
+  if (r > 0) {
+    const int64_t rows = nb - p.full_blocks * TILE;
+    int64_t h = 32 * ((rows + 32 * (int64_t)sms - 1) / (32 * (int64_t)sms));
+    if (h > TILE) h = TILE;
+    p.tail_h = (int)h;
+    p.tail_blocks = (rows + h - 1) / h;
+  }
+  return p;
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 trsm_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const double* __restrict__ ws,
-                 double* __restrict__ B, int64_t ldb, int64_t nb, double* __restrict__ scratch) {
+                 double* __restrict__ B, int64_t ldb, int64_t nb, double* __restrict__ scratch, int64_t full_blocks,
+                 int tail_h) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem_raw);
   pipe_init();
   const int ti = blockIdx.x;
-  double* Brow = B + (int64_t)ti * TILE * ldb;
-  const int valid = static_cast<int>(min64(TILE, nb - (int64_t)ti * TILE));
+  const int64_t row0 = ti < full_blocks ? (int64_t)ti * TILE : full_blocks * TILE + (ti - full_blocks) * (int64_t)tail_h;
+  double* Brow = B + row0 * ldb;
+  const int valid = static_cast<int>(min64(ti < full_blocks ? TILE : tail_h, nb - row0));
   const int nt = static_cast<int>((n + TILE - 1) / TILE);
   const double* flags = ws + (int64_t)nt * TILE * TILE;
   for (int j = 0; j < nt; ++j) {
@@ -764,7 +792,7 @@ trsm_rows_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const dou
     if (j > 0) {
       Acc acc;
       acc_zero(acc);
-      gemm_nt_mainloop(stages, Brow, ldb, valid, L + (int64_t)j * TILE * ldl, ldl, kb, j * TILE, acc);
+      gemm_nt_mainloop<4>(stages, Brow, ldb, valid, L + (int64_t)j * TILE * ldl, ldl, kb, j * TILE, acc);
       store_tile<1>(Brow + (int64_t)j * TILE, ldb, valid, kb, acc, false);
       __threadfence();
       __syncthreads();
@@ -1709,9 +1737,17 @@ extern "C" size_t gpar_potrf_workspace_bytes(int64_t n, int64_t nb, int64_t batc
   return (size_t)doubles * sizeof(double);
 }
 
+static int device_sms() {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 148;
+}
+
 extern "C" size_t gpar_trsm_rows_scratch_bytes(int64_t nb) {
   if (nb <= 0) return 0;
-  return (size_t)((nb + TILE - 1) / TILE) * TILE * TILE * sizeof(double);
+  const RowPlan p = trsm_row_plan(nb, device_sms());
+  return (size_t)(p.full_blocks + p.tail_blocks) * TILE * TILE * sizeof(double);  // one tile per row block
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -1891,8 +1927,10 @@ extern "C" int gpar_trsm_rows(const double* L, int64_t ldl, int64_t n, const dou
   if (!B || !aligned16(B) || (ldb & 1) || ldb < n) { set_error("gpar_trsm_rows: bad B"); return -5; }
   if (!scratch || !aligned16(scratch)) { set_error("gpar_trsm_rows: bad scratch"); return -8; }
   set_smem_attrs();
-  unsigned g = (unsigned)((nb + TILE - 1) / TILE);
-  trsm_rows_kernel<<<g, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(L, ldl, n, ws, B, ldb, nb, scratch);
+  const RowPlan p = trsm_row_plan(nb, device_sms());
+  unsigned g = (unsigned)(p.full_blocks + p.tail_blocks);
+  trsm_rows_kernel<<<g, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(L, ldl, n, ws, B, ldb, nb, scratch, p.full_blocks,
+                                                                  p.tail_h);
   return check_launch("gpar_trsm_rows");
 }
 

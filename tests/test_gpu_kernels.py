@@ -190,7 +190,10 @@ def test_potrf_batched(eng):
         assert np.linalg.norm(np.tril(got[b]) - Lref) / np.linalg.norm(Lref) <= 1e-11
 
 
-@pytest.mark.parametrize("n,nb", [(100, 5), (300, 260), (513, 129)])
+# nb beyond one wave of 128-row blocks (148 SMs): the rows left after the whole waves run as 32 / 64 / 96-row
+# blocks (trsm_row_plan): 100 -> 3 x 32 + 4; 27904 -> one wave + 140 x 64; 31761 -> one wave + 133 x 96 + 49
+@pytest.mark.parametrize("n,nb", [(100, 5), (300, 260), (513, 129), (300, 100), (200, 27904), (130, 31761),
+                                  (129, 148 * 128)])
 def test_trsm_rows_and_backsolve(eng, n, nb):
     rng = np.random.default_rng(n * 7 + nb)
     A = spd(n, rng)
@@ -216,6 +219,29 @@ def test_trsm_rows_and_backsolve(eng, n, nb):
     ld_ref, q_ref = 2 * np.sum(np.log(np.diag(Lref))), float(u @ u)
     got2 = out2.cpu().numpy()
     assert abs(got2[0] - ld_ref) <= 1e-11 * max(1, abs(ld_ref)) and abs(got2[1] - q_ref) <= 1e-12 * q_ref
+
+
+def test_trsm_rows_refined_tail_blocks(eng):
+    """Ill-conditioned diagonal tiles (refine flags set) with a tail of 32-row blocks: every block has its own
+    scratch tile for the refinement step; backward error at rounding level, rows bit-identical whatever block
+    they fall into (the same rows solved alone and inside a larger batch)."""
+    rng = np.random.default_rng(77)
+    n, nb = 300, 200
+    A = spd(n, rng, cond_noise=1e-9)
+    Ad = dev(eng, np.tril(A)).reshape(-1)
+    ws, info = eng.potrf(Ad, n, n)
+    assert int(info.cpu()[0]) == 0
+    assert ws.cpu().numpy()[3 * 128 * 128:3 * 128 * 128 + 3].any()  # refine flags set
+    L = np.tril(Ad.cpu().numpy().reshape(n, n))
+    B = rng.standard_normal((nb, n))
+    Bd = dev(eng, B).reshape(-1)
+    eng.trsm_rows(Ad, n, n, ws, Bd, n, nb)
+    X = Bd.cpu().numpy().reshape(nb, n)
+    assert np.linalg.norm(X @ L.T - B) / (np.linalg.norm(X) * np.linalg.norm(L)) <= 1e-13
+    big = np.concatenate([rng.standard_normal((148 * 128 + 40, n)), B[:70]])  # same rows, other block heights
+    Gd = dev(eng, big).reshape(-1)
+    eng.trsm_rows(Ad, n, n, ws, Gd, n, big.shape[0])
+    assert np.array_equal(Gd.cpu().numpy().reshape(-1, n)[-70:], X[:70])
 
 
 @pytest.mark.parametrize("n,k,batch", [(64, 10, 1), (300, 257, 1), (130, 520, 3)])
