@@ -89,8 +89,9 @@ class Engine:
     def chain_chunk(self, S, bytes_per_chain, tiles_per_chain=1, frac=0.6):
         """Number of diverged chains to process per pass (model.py:557-564 runs them one by one; the
         arithmetic is independent per chain): as many as fit into ``frac`` of the free device memory
-        (or ``GPAR_CHAIN_CHUNK_BYTES``), trimmed so that the row-tile count of a pass fills whole waves
-        of the SMs."""
+        (or ``GPAR_CHAIN_CHUNK_BYTES``), trimmed so that the row blocks of a pass fill the SMs: whole
+        waves of 128-row blocks plus one wave of 32 / 64 / 96-row blocks for the rest (``trsm_row_plan`` in
+        csrc/potrf.cu), which cost about 0.4 / 0.6 / 0.8 of a full wave (measured)."""
         budget = int(os.environ.get("GPAR_CHAIN_CHUNK_BYTES", 0)) or int(frac * self.free_bytes())
         hi = int(max(1, min(S, budget // max(int(bytes_per_chain), 1))))
         if hi >= S:
@@ -99,7 +100,9 @@ class Engine:
         best, best_eff = hi, 0.0
         for c in range(hi, max(hi * 3 // 4, 1) - 1, -1):
             t = c * max(int(tiles_per_chain), 1)
-            eff = t / float(-(-t // sms) * sms)
+            w, r = divmod(t, sms)
+            tail = 0.0 if r == 0 else (0.4, 0.6, 0.8, 1.0)[min(-(-(r * 4) // sms), 4) - 1]
+            eff = t / float((w + tail) * sms)
             if eff > best_eff + 1e-9:
                 best, best_eff = c, eff
         return int(best)
