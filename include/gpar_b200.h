@@ -129,7 +129,10 @@ int gpar_ipc_open(const unsigned char* handle64, void** ptr);
 int gpar_ipc_close(void* ptr);
 
 /* K4 -- B (nb x n) <- B L^-T given L and the `ws` of its gpar_potrf.  This is
- * (L^-1 K(x_a, x_))^T of PosteriorMean / PosteriorKernel. */
+ * (L^-1 K(x_a, x_))^T of PosteriorMean / PosteriorKernel.
+ * `scratch`: gpar_trsm_rows_scratch_bytes(nb) bytes on the CURRENT device (one tile per row block; the
+ * number of row blocks depends on the SM count: whole waves of 128-row blocks, then blocks of 32 / 64 / 96
+ * rows).  Rows are solved independently: the result does not depend on how they fall into blocks. */
 size_t gpar_trsm_rows_scratch_bytes(int64_t nb);
 int gpar_trsm_rows(const double* L, int64_t ldl, int64_t n, const double* ws, double* B, int64_t ldb,
                    int64_t nb, double* scratch, void* stream);
