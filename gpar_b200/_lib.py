@@ -102,6 +102,7 @@ DEBUG_HOOKS = {
     "gpar_debug_set_dataflow_prof": (_int, [_p]),
     "gpar_debug_decode_ticket": (_int, [_i64, _i64, _i64, _i64, _i64, C.POINTER(C.c_int32)]),
     "gpar_debug_diag_profile": (_int, [_p, _i64, _i64, _p, _p, _p, _p]),
+    "gpar_debug_trsm_row_plan": (_int, [_i64, _int, C.POINTER(C.c_int64)]),
 }
 DEBUG_PROBES = {
     "gpar_debug_latency_probe": (_int, [_p, _p]),

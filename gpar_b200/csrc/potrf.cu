@@ -2051,6 +2051,14 @@ extern "C" int gpar_debug_decode_ticket(int64_t n, int64_t nb, int64_t batch, in
   return (int)total;
 }
 
+// Debug: the row-block plan of gpar_trsm_rows for nb rows on `sms` SMs (host only).
+extern "C" int gpar_debug_trsm_row_plan(int64_t nb, int sms, int64_t* out3) {
+  if (nb <= 0 || sms <= 0 || !out3) return -1;
+  const RowPlan p = trsm_row_plan(nb, sms);
+  out3[0] = p.full_blocks; out3[1] = p.tail_blocks; out3[2] = p.tail_h;
+  return 0;
+}
+
 // Debug: phase timestamps (clock64) of the diagonal-tile factor on the leading 128 block of A.
 extern "C" int gpar_debug_diag_profile(double* A, int64_t lda, int64_t n, double* ws, int32_t* info, long long* prof,
                                        void* stream_) {

@@ -33,6 +33,9 @@ int gpar_debug_set_dataflow_prof(long long* prof);
  * tile row, tile column, K-part, number of K-parts of the tile (split-K in the tail of the sweep)}.
  * Returns the number of tickets. */
 int gpar_debug_decode_ticket(int64_t n, int64_t nb, int64_t batch, int64_t grid, int64_t t, int32_t* out6);
+/* Debug: row-block plan of gpar_trsm_rows for nb rows on `sms` SMs: out3 = {128-row blocks, tail blocks, tail
+ * block height}.  Host only. */
+int gpar_debug_trsm_row_plan(int64_t nb, int sms, int64_t* out3);
 /* Debug: clock64 phase timestamps (21 values) of the diagonal-tile factor on A[0:128, 0:128]. */
 int gpar_debug_diag_profile(double* A, int64_t lda, int64_t n, double* ws, int32_t* info, long long* prof,
                             void* stream);

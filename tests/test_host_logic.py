@@ -264,3 +264,34 @@ def test_regressor_reports_kernel_spec_limits_at_condition():
     with pytest.raises(ValueError, match="markov"):
         reg.condition(x, y)
     GPARRegressor(linear=True, nonlinear=True, markov=3).condition(x, y)
+
+
+# ---- row-block plan of gpar_trsm_rows (host function shared with the launch; no GPU) ----
+def test_trsm_row_plan_covers_rows_in_whole_waves_plus_one_tail_wave():
+    import ctypes as C
+
+    from gpar_b200 import _lib
+
+    lib = _lib.load()
+    out = (C.c_int64 * 3)()
+    rng = np.random.default_rng(0)
+    cases = [1, 4, 31, 32, 33, 100, 128, 129, 4096, 148 * 32, 148 * 32 + 1, 148 * 128 - 1, 148 * 128, 148 * 128 + 1,
+             65536, 20480, 102400, 27904, 31761] + [int(v) for v in rng.integers(1, 400000, 200)]
+    for sms in (148, 132, 7):
+        for nb in cases:
+            assert lib.gpar_debug_trsm_row_plan(nb, sms, out) == 0
+            full, tail, h = int(out[0]), int(out[1]), int(out[2])
+            assert full % sms == 0                                 # whole waves of 128-row blocks
+            rest = nb - full * 128
+            if tail == 0:                                          # they cover everything (last one may be ragged)
+                assert -128 < rest <= 0
+                continue
+            assert rest > 0
+            assert h in (32, 64, 96, 128) and 0 < tail <= sms      # one more wave
+            assert (tail - 1) * h < rest <= tail * h               # covers the rest exactly, last block ragged
+            if h > 32:                                             # the smallest height that fits one wave
+                assert -(-rest // (h - 32)) > sms
+    # the C5 per-rank pass on 8 GPUs: 512 row tiles -> 3 waves + 136 blocks of 64 rows
+    lib.gpar_debug_trsm_row_plan(65536, 148, out)
+    assert tuple(out) == (444, 136, 64)
+    assert lib.gpar_debug_trsm_row_plan(0, 148, out) != 0
