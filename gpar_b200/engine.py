@@ -23,6 +23,16 @@ def _even(n):
     return n + (n & 1)
 
 
+def wave_efficiency(tiles, sms):
+    """Fraction of the SMs' time a pass of ``tiles`` 128-row blocks keeps busy in ``gpar_trsm_rows``: whole
+    waves of one block per SM, then the rest as blocks of 32 / 64 / 96 / 128 rows in one more wave
+    (``trsm_row_plan`` in csrc/potrf.cu) that costs about 0.4 / 0.6 / 0.8 / 1.0 of a full one (measured on a
+    B200)."""
+    w, r = divmod(int(tiles), int(sms))
+    tail = 0.0 if r == 0 else (0.4, 0.6, 0.8, 1.0)[min(-(-(r * 4) // sms), 4) - 1]
+    return tiles / float((w + tail) * sms)
+
+
 class Engine:
     """Owns the library handle, the device and the launch counter."""
 
@@ -99,10 +109,7 @@ class Engine:
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         best, best_eff = hi, 0.0
         for c in range(hi, max(hi * 3 // 4, 1) - 1, -1):
-            t = c * max(int(tiles_per_chain), 1)
-            w, r = divmod(t, sms)
-            tail = 0.0 if r == 0 else (0.4, 0.6, 0.8, 1.0)[min(-(-(r * 4) // sms), 4) - 1]
-            eff = t / float((w + tail) * sms)
+            eff = wave_efficiency(c * max(int(tiles_per_chain), 1), sms)
             if eff > best_eff + 1e-9:
                 best, best_eff = c, eff
         return int(best)

@@ -295,3 +295,13 @@ def test_trsm_row_plan_covers_rows_in_whole_waves_plus_one_tail_wave():
     lib.gpar_debug_trsm_row_plan(65536, 148, out)
     assert tuple(out) == (444, 136, 64)
     assert lib.gpar_debug_trsm_row_plan(0, 148, out) != 0
+
+
+def test_wave_efficiency_model_of_the_chain_passes():
+    from gpar_b200.engine import wave_efficiency
+
+    assert wave_efficiency(148, 148) == 1.0 and wave_efficiency(296, 148) == 1.0
+    assert wave_efficiency(512, 148) == pytest.approx(512 / (3.6 * 148))      # 3 waves + 64-row tail blocks
+    assert wave_efficiency(149, 148) == pytest.approx(149 / (1.4 * 148))      # one block left: 32-row blocks
+    assert wave_efficiency(148 + 120, 148) == pytest.approx(268 / (2.0 * 148))  # too many rows left: a full wave
+    assert all(0.0 < wave_efficiency(t, 148) <= 1.0 + 1e-12 for t in range(1, 2000))
