@@ -304,3 +304,30 @@ def test_predict_device_transforms_match_host_path(which):
     # Q8: the mean of the un-transformed samples is not the un-transformed mean
     reg_id = GPARRegressor(**{**kw, "transform_y": (lambda v: v, lambda v: v)})
     assert np.all(lo <= hi) and np.all(np.isfinite(mean))
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_diverged_chains_in_memory_sized_passes_bit_identical(monkeypatch, sparse):
+    """Engine.chain_chunk: diverged chains (replace=False) run in passes when they do not fit the device memory
+    (C5 on one GPU: 137 GB of cross-covariances).  Forcing small passes through GPAR_CHAIN_CHUNK_BYTES must not
+    change a bit of any sample (dense and inducing-point layers; ragged last pass; trsm_rows tail blocks)."""
+    from gpar_b200 import GPARRegressor
+
+    data_kw, reg_kw = bench.CONFIGS["c2"]
+    kw = {**data_kw, "n": 600, "ns": 130, "S": 11}
+    data = bench.make_data(**kw)
+    extra = dict(x_ind=np.random.default_rng(4).uniform(0, 1, (40, kw["m"]))) if sparse else {}
+    reg = GPARRegressor(**reg_kw, **extra)
+    reg.condition(data["x"], data["y"])
+    monkeypatch.delenv("GPAR_CHAIN_CHUNK_BYTES", raising=False)
+    full = np.stack(reg.sample(data["xs"], num_samples=kw["S"], posterior=True, normals={"Z": data["Z"]}))
+    eng = reg._engine_of(None)
+    # ~4 chains per pass: 8 * ns * (ldc + ld) bytes per chain plus its share of the batched-factor workspace
+    per_chain = 8 * 130 * (130 + 600) + eng.lib.gpar_potrf_workspace_bytes(130, 0, 2) // 2
+    monkeypatch.setenv("GPAR_CHAIN_CHUNK_BYTES", str(4 * per_chain + 1000))
+    calls = []
+    orig = eng.chain_chunk
+    monkeypatch.setattr(eng, "chain_chunk", lambda *a, **k: calls.append(orig(*a, **k)) or calls[-1])
+    chunked = np.stack(reg.sample(data["xs"], num_samples=kw["S"], posterior=True, normals={"Z": data["Z"]}))
+    assert calls and max(calls) < kw["S"]  # the passes really were smaller than S
+    assert np.array_equal(full, chunked)
