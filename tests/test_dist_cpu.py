@@ -99,3 +99,45 @@ def test_potrf_layout_is_aligned_and_disjoint():
             end = off + size
         assert lay["bytes"] >= 8 * end
     assert [tile_row_owner(i, 2) for i in range(10)] == [0, 0, 0, 0, 1, 1, 1, 1, 0, 0]
+
+
+def _rng_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch
+
+    from gpar_b200.dist import chain_generator
+
+    torch.manual_seed(1234)  # SPMD programs seed every rank identically
+    S = 6
+    start, stop = chain_slice(S, rank, world)
+    gen = chain_generator("cpu", start)
+    mine = torch.randn(stop - start, 5, generator=gen, dtype=torch.float64)
+    # a second call draws a new base seed on rank 0 and broadcasts it: with the same chain offset every rank
+    # gets the same stream, i.e. the base really is shared and only the offset separates the ranks
+    other = chain_generator("cpu", 7)
+    theirs = torch.randn(3, 5, generator=other, dtype=torch.float64)
+    q.put((rank, mine.numpy(), theirs.numpy()))
+    dist.destroy_process_group()
+
+
+def test_chain_rng_streams_differ_across_identically_seeded_ranks_gloo_world2():
+    """dist.chain_generator: ranks seeded identically must not draw the same chains (the gathered set would hold
+    S / world distinct ones); the base seed is shared (drawn on rank 0, broadcast), the offset is the first chain."""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rng_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(2):
+        rank, mine, theirs = q.get()
+        got[rank] = (mine, theirs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert not np.array_equal(got[0][0], got[1][0])           # distinct chains on the two ranks
+    assert np.array_equal(got[0][1], got[1][1])               # same (base, offset) -> same stream on both ranks
+    assert not np.array_equal(got[0][1], got[0][0][:3])       # and a fresh base per call
